@@ -1,0 +1,172 @@
+/*
+ * regk.h — C-ABI of libregk.so, the B200-native replacement for registrar's
+ * per-record registration hot path (SURVEY.md §8 rows A1–A5).
+ *
+ * The reference has no FFI of its own (it is 100 % JavaScript); the entry
+ * points below are what an N-API addon for that path binds (see
+ * INTEGRATION.md and registrar_b200/napi/).  Each one names the reference
+ * code it replaces, relative to /root/reference:
+ *
+ *   regk_register_batch  <- lib/register.js:34-39   domainToPath()            (A1)
+ *                           lib/register.js:221-223 path.join(p, hostname)    (A2)
+ *                           lib/register.js:141-155 host-record object        (A3)
+ *                           lib/register.js:156-159 zk.create(n,_obj,...) ->
+ *                             zkplus JSON.stringify(_obj) -> UTF-8 bytes      (A4)
+ *                           (new) per-record output offsets                   (A5)
+ *   regk_set_types       <- lib/register.js:142,152 `type` / `_obj[type]` key
+ *   REGK_NODE_ALIAS      <- lib/register.js:223     aliases.map(domainToPath)
+ *
+ * Conventions: extern "C", plain pointers and sizes, no exceptions cross the
+ * boundary, every call returns a REGK_* status and leaves a message readable
+ * through regk_last_error().  There is NO CPU fallback: without a usable
+ * CUDA device regk_create() fails.
+ *
+ * Threading: a context is single-owner (one host thread at a time, one CUDA
+ * stream).  The N-API shim runs calls on a napi_async_work thread and
+ * resolves the Node errback on the main loop.
+ */
+#ifndef REGK_H
+#define REGK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REGK_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------ */
+#define REGK_OK                 0
+#define REGK_ERR_INVALID_ARG    1   /* NULL pointer, bad flag combination, misaligned device pointer */
+#define REGK_ERR_CUDA           2   /* CUDA runtime error; text in regk_last_error() */
+#define REGK_ERR_OUT_OF_DOMAIN  3   /* >=1 record outside the fenced input domain; nothing is returned */
+#define REGK_ERR_NOMEM          4
+#define REGK_ERR_STATE          5   /* e.g. type table not set, result already released */
+
+/* ---- batch flags -------------------------------------------------------- */
+#define REGK_IN_DEVICE   (1u << 0)  /* batch arrays are device pointers (16-byte aligned); else host memory */
+#define REGK_OUT_DEVICE  (1u << 1)  /* result arrays are device pointers; else library-owned pinned host memory */
+#define REGK_NODE_ALIAS  (1u << 2)  /* alias nodes: path = domainToPath(domain) un-normalised, no hostname
+                                       (lib/register.js:223); default = host nodes (A2, lib/register.js:222) */
+#define REGK_NO_JSON     (1u << 3)  /* paths only (skip A3/A4) */
+#define REGK_NO_PATH     (1u << 4)  /* payloads only (skip A1/A2) */
+
+/* ---- per-record validation bits (regk_result.bad_bits) ------------------ */
+#define REGK_BAD_DOMAIN_BYTE  (1u << 0)  /* byte >= 0x80 or '/' in a domain (JS toLowerCase / path.normalize
+                                            semantics are only restated for ASCII, slash-free labels) */
+#define REGK_BAD_HOST_BYTE    (1u << 1)  /* hostname empty, ".", "..", or has byte >= 0x80, NUL or '/' */
+#define REGK_BAD_ADDR_BYTE    (1u << 2)  /* address byte outside 0x20..0x7f or needing a JSON escape (" or \) */
+#define REGK_BAD_TYPE_ID      (1u << 3)  /* type_id >= number of types set */
+#define REGK_BAD_TOO_LARGE    (1u << 4)  /* a single record's path or payload exceeds 2^31 bytes */
+
+#define REGK_TTL_ABSENT  INT32_MIN      /* registration.ttl === undefined -> key omitted (register.js:144) */
+
+typedef struct regk_ctx regk_ctx;
+
+/*
+ * One batch of service records, struct-of-arrays.  All offset arrays are CSR
+ * style with n+1 entries, offsets in bytes (or elements for ports_off)
+ * relative to the matching *_bytes / ports base.
+ */
+typedef struct regk_batch {
+    uint64_t        n;              /* number of records */
+    uint32_t        flags;          /* REGK_IN_DEVICE | REGK_OUT_DEVICE | REGK_NODE_ALIAS | ... */
+    uint32_t        host_stride;    /* used when host_off == NULL: hostname i = host_bytes[i*stride, +stride) */
+
+    /* Lengths of the packed arrays (== the last entry of the matching offset array).  Required for
+       device-resident batches (the library does not read device memory to size its outputs);
+       may be 0 for host batches, the library then reads them from the offset arrays. */
+    uint64_t        domain_bytes_len;
+    uint64_t        host_bytes_len;
+    uint64_t        addr_bytes_len;
+    uint64_t        ports_len;      /* elements */
+
+    const uint8_t  *domain_bytes;   /* opts.domain (or one alias) per record, packed */
+    const uint32_t *domain_off;     /* [n+1] */
+
+    const uint8_t  *host_bytes;     /* os.hostname() per record (zone UUID in Triton); ignored for alias nodes */
+    const uint32_t *host_off;       /* [n+1] or NULL for fixed stride */
+
+    const uint8_t  *type_id;        /* [n] index into the table given to regk_set_types() */
+
+    const uint8_t  *addr_bytes;     /* opts.adminIp per record, packed */
+    const uint32_t *addr_off;       /* [n+1] */
+
+    const int32_t  *ttl;            /* [n]; REGK_TTL_ABSENT = undefined */
+
+    const uint32_t *ports_off;      /* [n+1] element offsets into ports, or NULL = no record has ports */
+    const uint32_t *ports;          /* registration.ports (or [service.service.port]) values */
+    const uint8_t  *ports_present;  /* [n] or NULL.  NULL: ports key present iff k>0.  Non-NULL: !=0 means
+                                       present, so an empty array is emitted as "ports":[] (register.js:146) */
+} regk_batch;
+
+/*
+ * Result views.  path_bytes[path_off[i] .. path_off[i+1]) is znode path i,
+ * json_bytes[json_off[i] .. json_off[i+1]) is payload i (what zkplus would
+ * hand to ZooKeeper).  Owned by the context until regk_release() or the next
+ * regk_register_batch() on the same context with the same result slot.
+ */
+typedef struct regk_result {
+    uint64_t        n;
+    uint32_t        flags;          /* REGK_OUT_DEVICE if the pointers below are device pointers */
+    uint32_t        bad_bits;       /* OR of REGK_BAD_* over all records (0 on success) */
+    uint64_t        first_bad;      /* smallest offending record index when bad_bits != 0 */
+    uint8_t        *path_bytes;
+    uint64_t       *path_off;       /* [n+1] */
+    uint64_t        path_total;     /* == path_off[n] */
+    uint8_t        *json_bytes;
+    uint64_t       *json_off;       /* [n+1] */
+    uint64_t        json_total;     /* == json_off[n] */
+    float           kernel_ms;      /* device time of the path+payload kernels (CUDA events on the ctx stream) */
+    float           path_kernel_ms;
+    float           json_kernel_ms;
+    uint32_t        launches;       /* kernels launched by this call */
+    void           *opaque;         /* library bookkeeping */
+} regk_result;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+int         regk_abi_version(void);
+int         regk_create(int device, regk_ctx **out);   /* binds one CUDA device; fails if none */
+void        regk_destroy(regk_ctx *ctx);
+const char *regk_last_error(const regk_ctx *ctx);      /* ctx may be NULL: error of the last failed regk_create */
+
+/* Run on a caller-supplied cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+int         regk_set_stream(regk_ctx *ctx, void *cuda_stream);
+
+/*
+ * Record-type table (registration.type values).  Strings are arbitrary UTF-8;
+ * JSON escaping (ECMA-262 QuoteJSONString) is applied here, on the host, once.
+ * Rejected (REGK_ERR_OUT_OF_DOMAIN): "type", "address", "ttl" (the dynamic key
+ * would overwrite a fixed one, register.js:152) and canonical array-index
+ * strings ("0", "42": V8 orders integer keys first).
+ */
+int         regk_set_types(regk_ctx *ctx, const char *const *types, const uint32_t *lens, uint32_t ntypes);
+
+/* ---- the hot path ------------------------------------------------------ */
+int         regk_register_batch(regk_ctx *ctx, const regk_batch *batch, regk_result *result);
+/* With option "async" = 1 regk_register_batch() only enqueues; regk_finish() waits for that batch,
+   fills totals / validation / timings and returns its status.  (Synchronous mode calls it itself.) */
+int         regk_finish(regk_ctx *ctx, regk_result *result);
+int         regk_release(regk_ctx *ctx, regk_result *result);
+
+/* Pinned host memory for callers that want zero-staging H2D/D2H. */
+void       *regk_host_alloc(regk_ctx *ctx, size_t bytes);
+void        regk_host_free(regk_ctx *ctx, void *p);
+
+/* Device memory helpers for non-CUDA hosts (Node, ctypes). */
+void       *regk_dev_alloc(regk_ctx *ctx, size_t bytes);
+void        regk_dev_free(regk_ctx *ctx, void *p);
+int         regk_memcpy_h2d(regk_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int         regk_memcpy_d2h(regk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int         regk_sync(regk_ctx *ctx);
+
+/* Tuning knobs (kernel variant selection for A/B measurement); see DESIGN.md. */
+int         regk_set_option(regk_ctx *ctx, const char *name, int64_t value);
+int64_t     regk_get_option(const regk_ctx *ctx, const char *name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGK_H */

@@ -1,0 +1,169 @@
+"""ctypes front end of oracle/regoracle.c — the CPU parity oracle.
+
+TEST INFRASTRUCTURE ONLY (see the header of regoracle.c): imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+Nothing under registrar_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class _Batch(C.Structure):          # mirrors regk_batch (include/regk.h)
+    _fields_ = [("n", C.c_uint64), ("flags", C.c_uint32), ("host_stride", C.c_uint32),
+                ("domain_bytes_len", C.c_uint64), ("host_bytes_len", C.c_uint64),
+                ("addr_bytes_len", C.c_uint64), ("ports_len", C.c_uint64),
+                ("domain_bytes", C.c_void_p), ("domain_off", C.c_void_p),
+                ("host_bytes", C.c_void_p), ("host_off", C.c_void_p),
+                ("type_id", C.c_void_p),
+                ("addr_bytes", C.c_void_p), ("addr_off", C.c_void_p),
+                ("ttl", C.c_void_p),
+                ("ports_off", C.c_void_p), ("ports", C.c_void_p), ("ports_present", C.c_void_p)]
+
+
+class _Types(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("str", C.POINTER(C.c_char_p)), ("len", C.POINTER(C.c_uint32))]
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with gcc (seconds)."""
+    so = os.path.join(_HERE, "libregoracle.so")
+    src = os.path.join(_HERE, "regoracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-Wall", "-o", so, src])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        for name in ("ro_domain_to_path", "ro_posix_normalize", "ro_posix_join2", "ro_posix_dirname",
+                     "ro_host_node_path", "ro_quote_json_string", "ro_host_record_json", "ro_path_len",
+                     "ro_json_len"):
+            getattr(_LIB, name).restype = C.c_size_t
+        _LIB.ro_register_batch.restype = C.c_uint32
+        _LIB.ro_validate_record.restype = C.c_uint32
+        _LIB.ro_max_threads.restype = C.c_int
+        _LIB.ro_free.restype = None
+    return _LIB
+
+
+def _buf(n):
+    return (C.c_uint8 * max(n, 1))()
+
+
+def domain_to_path(domain: bytes) -> bytes:
+    out = _buf(len(domain) + 2)
+    n = lib().ro_domain_to_path(domain, C.c_size_t(len(domain)), out)
+    return bytes(out[:n])
+
+
+def posix_normalize(p: bytes) -> bytes:
+    out = _buf(len(p) + 2)
+    n = lib().ro_posix_normalize(p, C.c_size_t(len(p)), out)
+    return bytes(out[:n])
+
+
+def posix_join2(a: bytes, b: bytes) -> bytes:
+    out = _buf(len(a) + len(b) + 3)
+    n = lib().ro_posix_join2(a, C.c_size_t(len(a)), b, C.c_size_t(len(b)), out)
+    return bytes(out[:n])
+
+
+def posix_dirname(p: bytes) -> bytes:
+    out = _buf(len(p) + 2)
+    n = lib().ro_posix_dirname(p, C.c_size_t(len(p)), out)
+    return bytes(out[:n])
+
+
+def host_node_path(domain: bytes, hostname: bytes) -> bytes:
+    out = _buf(len(domain) + len(hostname) + 4)
+    n = lib().ro_host_node_path(domain, C.c_size_t(len(domain)), hostname, C.c_size_t(len(hostname)), out)
+    return bytes(out[:n])
+
+
+def quote_json_string(s: bytes) -> bytes:
+    out = _buf(6 * len(s) + 2)
+    n = lib().ro_quote_json_string(s, C.c_size_t(len(s)), out)
+    return bytes(out[:n])
+
+
+def host_record_json(type_: bytes, address: bytes, ttl=None, ports=None) -> bytes:
+    k = 0 if ports is None else len(ports)
+    arr = (C.c_uint32 * max(k, 1))(*(ports or []))
+    out = _buf(64 + 12 * (len(type_) + len(address)) + 11 * (k + 1))
+    n = lib().ro_host_record_json(type_, C.c_size_t(len(type_)), address, C.c_size_t(len(address)),
+                                  C.c_int(ttl is not None), C.c_int32(0 if ttl is None else ttl),
+                                  C.c_int(ports is not None), arr, C.c_size_t(k), out)
+    return bytes(out[:n])
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c_batch(b, flags_extra=0):
+    flags = ((1 << 2) if b.alias else 0) | flags_extra       # REGK_NODE_ALIAS
+    keep = [np.ascontiguousarray(x) if x is not None else None for x in (
+        b.domain_bytes, b.domain_off, b.host_bytes, b.host_off, b.type_id, b.addr_bytes, b.addr_off, b.ttl,
+        b.ports_off, b.ports, b.ports_present)]
+    cb = _Batch(n=b.n, flags=flags, host_stride=b.host_stride, domain_bytes=_ptr(keep[0]),
+                domain_off=_ptr(keep[1]), host_bytes=_ptr(keep[2]), host_off=_ptr(keep[3]),
+                type_id=_ptr(keep[4]), addr_bytes=_ptr(keep[5]), addr_off=_ptr(keep[6]), ttl=_ptr(keep[7]),
+                ports_off=_ptr(keep[8]), ports=_ptr(keep[9]), ports_present=_ptr(keep[10]))
+    tstr = (C.c_char_p * max(len(b.types), 1))(*b.types)
+    tlen = (C.c_uint32 * max(len(b.types), 1))(*[len(t) for t in b.types])
+    ct = _Types(n=len(b.types), str=tstr, len=tlen)
+    return cb, ct, (keep, tstr, tlen)
+
+
+class OracleResult:
+    __slots__ = ("n", "path_bytes", "path_off", "json_bytes", "json_off", "bad_bits", "first_bad", "seconds")
+
+    def path(self, i):
+        return bytes(self.path_bytes[int(self.path_off[i]):int(self.path_off[i + 1])])
+
+    def json(self, i):
+        return bytes(self.json_bytes[int(self.json_off[i]):int(self.json_off[i + 1])])
+
+
+def register_batch(batch, threads: int = 0, flags_extra: int = 0) -> OracleResult:
+    """Run the C oracle over a host RecordBatch.  threads <= 0: all cores."""
+    L = lib()
+    cb, ct, keep = _c_batch(batch, flags_extra)
+    n = batch.n
+    poff = np.zeros(n + 1, np.uint64)
+    joff = np.zeros(n + 1, np.uint64)
+    pb = C.POINTER(C.c_uint8)()
+    jb = C.POINTER(C.c_uint8)()
+    fb = C.c_uint64(0)
+    t0 = time.perf_counter()
+    bad = L.ro_register_batch(C.byref(cb), C.byref(ct), C.c_int(threads), C.byref(pb), _ptr(poff),
+                              C.byref(jb), _ptr(joff), C.byref(fb))
+    dt = time.perf_counter() - t0
+    r = OracleResult()
+    r.n = n
+    r.seconds = dt
+    r.path_off, r.json_off = poff, joff
+    pt, jt = int(poff[-1]), int(joff[-1])
+    r.path_bytes = np.ctypeslib.as_array(pb, shape=(max(pt, 1),))[:pt].copy()
+    r.json_bytes = np.ctypeslib.as_array(jb, shape=(max(jt, 1),))[:jt].copy()
+    L.ro_free(pb)
+    L.ro_free(jb)
+    r.bad_bits = int(bad)
+    r.first_bad = int(fb.value) if bad else None
+    del keep
+    return r
+
+
+def max_threads() -> int:
+    return int(lib().ro_max_threads())

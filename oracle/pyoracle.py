@@ -1,0 +1,111 @@
+"""Independent pure-Python restatement of the hot path (small cases only).
+
+TEST INFRASTRUCTURE ONLY.  A second, deliberately different implementation of
+the same reference semantics, used to triangulate oracle/regoracle.c:
+string methods for the path half, ``json.dumps`` for the payload bytes (its
+compact form equals ECMA-262 JSON.stringify for str/int/list/dict in the fenced
+domain: insertion order, no whitespace, same escapes, ensure_ascii=False).
+
+Citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import json
+from collections import OrderedDict
+
+
+def domain_to_path(domain: str) -> str:
+    # lib/register.js:38  '/' + domain.toLowerCase().split('.').reverse().join('/')
+    assert isinstance(domain, str), "domain (string) is required"       # assert.string, :35
+    return "/" + "/".join(reversed(domain.lower().split(".")))
+
+
+def node_normalize(p: str) -> str:
+    # node core posix path.normalize (documented algorithm)
+    if p == "":
+        return "."
+    is_abs = p.startswith("/")
+    trailing = p.endswith("/")
+    out = []
+    for seg in p.split("/"):
+        if seg == "" or seg == ".":
+            continue
+        if seg == "..":
+            if out and out[-1] != "..":
+                out.pop()
+            elif not is_abs:
+                out.append("..")
+            continue
+        out.append(seg)
+    s = "/".join(out)
+    if not s and not is_abs:
+        s = "."
+    if s and trailing:
+        s += "/"
+    return ("/" if is_abs else "") + s
+
+
+def node_join(*parts: str) -> str:
+    joined = "/".join(x for x in parts if x)
+    return node_normalize(joined) if joined else "."
+
+
+def node_dirname(p: str) -> str:
+    if p == "":
+        return "."
+    stripped = p.rstrip("/")
+    if stripped == "":
+        return "/"
+    i = stripped.rfind("/")
+    if i < 0:
+        return "."
+    head = stripped[:i].rstrip("/")
+    if head == "":
+        return "//" if p.startswith("/") and i == 1 else "/"
+    return head
+
+
+def host_node_path(domain: str, hostname: str) -> str:
+    # lib/register.js:222  path.join(p, os.hostname())
+    return node_join(domain_to_path(domain), hostname)
+
+
+def host_record_object(type_: str, address: str, ttl=None, ports=None) -> "OrderedDict":
+    # lib/register.js:141-155; `undefined` members are dropped by JSON.stringify
+    obj = OrderedDict()
+    obj["type"] = type_
+    obj["address"] = address
+    if ttl is not None:
+        obj["ttl"] = ttl
+    inner = OrderedDict()
+    inner["address"] = address
+    if ports is not None:
+        inner["ports"] = list(ports)
+    obj[type_] = inner          # dynamic key, :152 (collides for type in {type,address,ttl}: fenced out)
+    return obj
+
+
+def json_stringify(obj) -> bytes:
+    return json.dumps(obj, separators=(",", ":"), ensure_ascii=False).encode("utf-8")
+
+
+def host_record_json(type_: str, address: str, ttl=None, ports=None) -> bytes:
+    return json_stringify(host_record_object(type_, address, ttl, ports))
+
+
+def service_record_json(service: dict) -> bytes:
+    # lib/register.js:58-61  {type:'service', service: opts.registration.service}
+    obj = OrderedDict()
+    obj["type"] = "service"
+    obj["service"] = service
+    return json_stringify(obj)
+
+
+def register_record(rec: dict, alias: bool = False):
+    """(path bytes, payload bytes) for one record dict as used by RecordBatch.from_records."""
+    dec = lambda x: x.decode("utf-8") if isinstance(x, (bytes, bytearray)) else x
+    domain = dec(rec["domain"])
+    path = domain_to_path(domain) if alias else host_node_path(domain, dec(rec["hostname"]))
+    addr = dec(rec.get("address", rec.get("adminIp", "")))
+    payload = host_record_json(dec(rec["type"]), addr, rec.get("ttl"), rec.get("ports"))
+    return path.encode("utf-8"), payload

@@ -1,0 +1,282 @@
+"""ctypes binding of libregk.so (include/regk.h).
+
+This is the only way record bytes are produced in this package: every call
+goes through the C-ABI into the sm_100a kernels.  There is deliberately no
+Python/NumPy implementation of the path here — if the shared library is not
+built, or no CUDA device is usable, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .batch import (FLAG_IN_DEVICE, FLAG_NODE_ALIAS, FLAG_NO_JSON, FLAG_NO_PATH, FLAG_OUT_DEVICE,
+                    RecordBatch)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libregk.so")
+
+REGK_OK = 0
+REGK_ERR_INVALID_ARG = 1
+REGK_ERR_CUDA = 2
+REGK_ERR_OUT_OF_DOMAIN = 3
+REGK_ERR_NOMEM = 4
+REGK_ERR_STATE = 5
+
+
+class RegkError(RuntimeError):
+    def __init__(self, code: int, message: str, result=None):
+        super().__init__("regk error %d: %s" % (code, message))
+        self.code = code
+        self.message = message
+        self.result = result
+
+
+class OutOfDomainError(RegkError):
+    """A record is outside the fenced input domain (REGK_ERR_OUT_OF_DOMAIN)."""
+
+
+class CBatch(C.Structure):           # regk_batch
+    _fields_ = [("n", C.c_uint64), ("flags", C.c_uint32), ("host_stride", C.c_uint32),
+                ("domain_bytes_len", C.c_uint64), ("host_bytes_len", C.c_uint64),
+                ("addr_bytes_len", C.c_uint64), ("ports_len", C.c_uint64),
+                ("domain_bytes", C.c_void_p), ("domain_off", C.c_void_p),
+                ("host_bytes", C.c_void_p), ("host_off", C.c_void_p),
+                ("type_id", C.c_void_p),
+                ("addr_bytes", C.c_void_p), ("addr_off", C.c_void_p),
+                ("ttl", C.c_void_p),
+                ("ports_off", C.c_void_p), ("ports", C.c_void_p), ("ports_present", C.c_void_p)]
+
+
+class CResult(C.Structure):          # regk_result
+    _fields_ = [("n", C.c_uint64), ("flags", C.c_uint32), ("bad_bits", C.c_uint32),
+                ("first_bad", C.c_uint64),
+                ("path_bytes", C.c_void_p), ("path_off", C.c_void_p), ("path_total", C.c_uint64),
+                ("json_bytes", C.c_void_p), ("json_off", C.c_void_p), ("json_total", C.c_uint64),
+                ("kernel_ms", C.c_float), ("path_kernel_ms", C.c_float), ("json_kernel_ms", C.c_float),
+                ("launches", C.c_uint32), ("opaque", C.c_void_p)]
+
+
+EXPORTS = ["regk_abi_version", "regk_create", "regk_destroy", "regk_last_error", "regk_set_stream",
+           "regk_set_types", "regk_register_batch", "regk_finish", "regk_release", "regk_host_alloc",
+           "regk_host_free", "regk_dev_alloc", "regk_dev_free", "regk_memcpy_h2d", "regk_memcpy_d2h",
+           "regk_sync", "regk_set_option", "regk_get_option"]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libregk.so and type its entry points; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "registrar_b200: %s is missing — build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU fallback for the registration path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, u64, i64, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int64, C.c_size_t
+    lib.regk_abi_version.restype = C.c_int
+    lib.regk_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.regk_destroy.argtypes = [vp]
+    lib.regk_destroy.restype = None
+    lib.regk_last_error.argtypes = [vp]
+    lib.regk_last_error.restype = C.c_char_p
+    lib.regk_set_stream.argtypes = [vp, vp]
+    lib.regk_set_types.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(u32), u32]
+    lib.regk_register_batch.argtypes = [vp, C.POINTER(CBatch), C.POINTER(CResult)]
+    lib.regk_finish.argtypes = [vp, C.POINTER(CResult)]
+    lib.regk_release.argtypes = [vp, C.POINTER(CResult)]
+    lib.regk_host_alloc.argtypes = [vp, sz]
+    lib.regk_host_alloc.restype = vp
+    lib.regk_host_free.argtypes = [vp, vp]
+    lib.regk_host_free.restype = None
+    lib.regk_dev_alloc.argtypes = [vp, sz]
+    lib.regk_dev_alloc.restype = vp
+    lib.regk_dev_free.argtypes = [vp, vp]
+    lib.regk_dev_free.restype = None
+    lib.regk_memcpy_h2d.argtypes = [vp, vp, vp, sz]
+    lib.regk_memcpy_d2h.argtypes = [vp, vp, vp, sz]
+    lib.regk_sync.argtypes = [vp]
+    lib.regk_set_option.argtypes = [vp, C.c_char_p, i64]
+    lib.regk_get_option.argtypes = [vp, C.c_char_p]
+    lib.regk_get_option.restype = i64
+    _lib = lib
+    return lib
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def host_cbatch(b: RecordBatch, flags: int = 0):
+    """regk_batch over the NumPy arrays of a host RecordBatch.  Returns (struct, keepalive)."""
+    keep = [None if x is None else np.ascontiguousarray(x) for x in (
+        b.domain_bytes, b.domain_off, b.host_bytes, b.host_off, b.type_id, b.addr_bytes, b.addr_off, b.ttl,
+        b.ports_off, b.ports, b.ports_present)]
+    n = b.n
+    cb = CBatch(
+        n=n, flags=flags | (FLAG_NODE_ALIAS if b.alias else 0), host_stride=b.host_stride,
+        domain_bytes_len=int(b.domain_off[-1]) if n else 0,
+        host_bytes_len=0 if b.alias else (int(b.host_off[-1]) if b.host_off is not None else n * b.host_stride),
+        addr_bytes_len=int(b.addr_off[-1]) if n else 0,
+        ports_len=int(b.ports_off[-1]) if (b.ports_off is not None and n) else 0,
+        domain_bytes=_np_ptr(keep[0]), domain_off=_np_ptr(keep[1]), host_bytes=_np_ptr(keep[2]),
+        host_off=_np_ptr(keep[3]), type_id=_np_ptr(keep[4]), addr_bytes=_np_ptr(keep[5]),
+        addr_off=_np_ptr(keep[6]), ttl=_np_ptr(keep[7]), ports_off=_np_ptr(keep[8]), ports=_np_ptr(keep[9]),
+        ports_present=_np_ptr(keep[10]))
+    return cb, keep
+
+
+class HostResult:
+    """Host copy of a regk_result (NumPy views are copied out of the library's pinned buffers
+    unless copy=False)."""
+
+    def __init__(self, n, path_bytes, path_off, json_bytes, json_off, kernel_ms, path_ms, json_ms, launches):
+        self.n = n
+        self.path_bytes, self.path_off = path_bytes, path_off
+        self.json_bytes, self.json_off = json_bytes, json_off
+        self.kernel_ms, self.path_kernel_ms, self.json_kernel_ms = kernel_ms, path_ms, json_ms
+        self.launches = launches
+
+    @property
+    def path_total(self):
+        return int(self.path_off[-1])
+
+    @property
+    def json_total(self):
+        return int(self.json_off[-1])
+
+    def path(self, i: int) -> bytes:
+        return bytes(self.path_bytes[int(self.path_off[i]):int(self.path_off[i + 1])])
+
+    def json(self, i: int) -> bytes:
+        return bytes(self.json_bytes[int(self.json_off[i]):int(self.json_off[i + 1])])
+
+
+def _as_np(ptr, count, dtype):
+    if count == 0 or not ptr:
+        return np.zeros(0, dtype)
+    buf = (C.c_uint8 * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count)
+
+
+class Context:
+    """One regk_ctx: one CUDA device, one stream, single owner thread."""
+
+    def __init__(self, device: int = 0, types=None):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.regk_create(device, C.byref(h))
+        if rc != REGK_OK:
+            raise RegkError(rc, (self._lib.regk_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self._types = None
+        if types is not None:
+            self.set_types(types)
+
+    # -- lifecycle --
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.regk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self) -> str:
+        return (self._lib.regk_last_error(self._h) or b"").decode()
+
+    def _check(self, rc, result=None):
+        if rc == REGK_OK:
+            return
+        cls = OutOfDomainError if rc == REGK_ERR_OUT_OF_DOMAIN else RegkError
+        raise cls(rc, self._err(), result)
+
+    # -- configuration --
+    def set_types(self, types):
+        tl = [t if isinstance(t, (bytes, bytearray)) else str(t).encode("utf-8") for t in types]
+        if self._types == tl:
+            return
+        arr = (C.c_char_p * max(len(tl), 1))(*tl)
+        lens = (C.c_uint32 * max(len(tl), 1))(*[len(t) for t in tl])
+        self._check(self._lib.regk_set_types(self._h, arr, lens, len(tl)))
+        self._types = tl
+
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.regk_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        return int(self._lib.regk_get_option(self._h, name.encode()))
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.regk_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def sync(self):
+        self._check(self._lib.regk_sync(self._h))
+
+    # -- the hot path, host buffers in / host buffers out --
+    def register_batch(self, batch: RecordBatch, paths: bool = True, payloads: bool = True,
+                       copy: bool = True) -> HostResult:
+        """Host RecordBatch -> HostResult through regk_register_batch (H2D, kernels, D2H)."""
+        self.set_types(batch.types)
+        flags = (0 if paths else FLAG_NO_PATH) | (0 if payloads else FLAG_NO_JSON)
+        cb, keep = host_cbatch(batch, flags)
+        res = CResult()
+        rc = self._lib.regk_register_batch(self._h, C.byref(cb), C.byref(res))
+        del keep
+        if rc != REGK_OK:
+            self._check(rc, res)
+        n = int(res.n)
+        cp = (lambda a: a.copy()) if copy else (lambda a: a)
+        out = HostResult(
+            n, cp(_as_np(res.path_bytes, int(res.path_total), np.uint8)), cp(_as_np(res.path_off, n + 1, np.uint64)),
+            cp(_as_np(res.json_bytes, int(res.json_total), np.uint8)), cp(_as_np(res.json_off, n + 1, np.uint64)),
+            float(res.kernel_ms), float(res.path_kernel_ms), float(res.json_kernel_ms), int(res.launches))
+        self._lib.regk_release(self._h, C.byref(res))
+        return out
+
+    # -- raw access for device-resident callers (bench.py, multi-GPU host layer) --
+    def register_raw(self, cbatch: CBatch, cres: Optional[CResult] = None) -> CResult:
+        res = cres if cres is not None else CResult()
+        rc = self._lib.regk_register_batch(self._h, C.byref(cbatch), C.byref(res))
+        self._check(rc, res)
+        return res
+
+    def finish(self, cres: CResult) -> CResult:
+        self._check(self._lib.regk_finish(self._h, C.byref(cres)), cres)
+        return cres
+
+    def host_alloc(self, nbytes: int) -> int:
+        p = self._lib.regk_host_alloc(self._h, nbytes)
+        if not p:
+            raise MemoryError("regk_host_alloc(%d) failed" % nbytes)
+        return p
+
+    def host_free(self, p: int):
+        self._lib.regk_host_free(self._h, C.c_void_p(p))
+
+    def pinned_array(self, shape, dtype) -> np.ndarray:
+        """NumPy array in library-pinned host memory (lives until host_free(arr.ctypes.data))."""
+        dt = np.dtype(dtype)
+        count = int(np.prod(shape))
+        p = self.host_alloc(max(count * dt.itemsize, 1))
+        buf = (C.c_uint8 * (count * dt.itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx

@@ -1,0 +1,654 @@
+/*
+ * regk_api.cu — C-ABI (include/regk.h) over the sm_100a kernels.
+ *
+ * Host-side plumbing only: argument checks, device buffers, the per-type JSON
+ * fragment table, launch configuration, status read-back.  All record bytes
+ * are produced by the kernels in regk_kernels.cuh; there is no CPU
+ * implementation of the path in this library.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/regk.h"
+#include "regk_kernels.cuh"
+#include "regk_types.hpp"
+
+using namespace regk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct regk_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;              /* the stream work is enqueued on */
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    std::string err;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+
+    /* type table */
+    std::vector<std::string> types;             /* raw */
+    std::vector<uint8_t> blob_host;             /* TypeFrag[] + fragments, padded to 16 */
+    DevBuf blob_dev;
+    uint32_t max_type_q = 0;                    /* longest escaped type */
+
+    /* device staging of host batches */
+    DevBuf in[11];
+    /* outputs */
+    DevBuf path_bytes, path_off, json_bytes, json_off;
+    HostBuf h_path_bytes, h_path_off, h_json_bytes, h_json_off;
+    /* workspace: DevStatus | tickets | tile status */
+    DevBuf work;
+    DevStatus *h_status = nullptr;              /* pinned */
+
+    /* pending batch (single slot) */
+    bool pending = false;
+    bool timing_valid = false;
+    uint64_t pend_n = 0;
+    uint32_t pend_flags = 0;
+    uint32_t pend_launches = 0;
+
+    std::map<std::string, int64_t> opt;
+};
+
+namespace {
+
+int fail(regk_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c)
+        c->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, REGK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                __FILE__, __LINE__);                                                               \
+    } while (0)
+
+int ensure_dev(regk_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes <= b.cap)
+        return REGK_OK;
+    if (b.p)
+        CK(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8;            /* a little slack so slowly growing batches do not thrash */
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess)
+        return fail(ctx, REGK_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    b.cap = want;
+    return REGK_OK;
+}
+
+int ensure_host(regk_ctx *ctx, HostBuf &b, size_t bytes)
+{
+    bytes = (bytes + 4095) & ~(size_t)4095;
+    if (bytes <= b.cap)
+        return REGK_OK;
+    if (b.p)
+        CK(cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    cudaError_t e = cudaMallocHost(&b.p, bytes);
+    if (e != cudaSuccess)
+        return fail(ctx, REGK_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    b.cap = bytes;
+    return REGK_OK;
+}
+
+int64_t opt_get(const regk_ctx *c, const char *name, int64_t dflt)
+{
+    auto it = c->opt.find(name);
+    return it == c->opt.end() ? dflt : it->second;
+}
+
+size_t align16(size_t v)
+{
+    return (v + 15) & ~(size_t)15;
+}
+
+}  // namespace
+
+extern "C" {
+
+int regk_abi_version(void)
+{
+    return REGK_ABI_VERSION;
+}
+
+const char *regk_last_error(const regk_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+int regk_create(int device, regk_ctx **out)
+{
+    regk_ctx *ctx = nullptr;
+    if (!out)
+        return fail(nullptr, REGK_ERR_INVALID_ARG, "regk_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, REGK_ERR_CUDA, "regk_create: no CUDA device (%s); this library has no CPU fallback",
+            e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev)
+        return fail(nullptr, REGK_ERR_INVALID_ARG, "regk_create: device %d out of range (0..%d)", device, ndev - 1);
+    ctx = new regk_ctx();
+    ctx->device = device;
+#define CKC(call)                                                                               \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            int rc_ = fail(nullptr, REGK_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+            delete ctx;                                                                         \
+            return rc_;                                                                         \
+        }                                                                                       \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        int rc = fail(nullptr, REGK_ERR_CUDA, "regk_create: device %d is sm_%d%d; this build targets sm_100a (B200)",
+            device, prop.major, prop.minor);
+        delete ctx;
+        return rc;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    for (auto &ev : ctx->ev)
+        CKC(cudaEventCreate(&ev));
+    CKC(cudaMallocHost((void **)&ctx->h_status, sizeof(DevStatus)));
+    memset(ctx->h_status, 0, sizeof(DevStatus));
+#undef CKC
+    *out = ctx;
+    return REGK_OK;
+}
+
+void regk_destroy(regk_ctx *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->in)
+        if (b.p)
+            cudaFree(b.p);
+    for (DevBuf *b : {&ctx->blob_dev, &ctx->path_bytes, &ctx->path_off, &ctx->json_bytes, &ctx->json_off, &ctx->work})
+        if (b->p)
+            cudaFree(b->p);
+    for (HostBuf *b : {&ctx->h_path_bytes, &ctx->h_path_off, &ctx->h_json_bytes, &ctx->h_json_off})
+        if (b->p)
+            cudaFreeHost(b->p);
+    if (ctx->h_status)
+        cudaFreeHost(ctx->h_status);
+    for (auto &ev : ctx->ev)
+        if (ev)
+            cudaEventDestroy(ev);
+    if (ctx->own_stream)
+        cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int regk_set_stream(regk_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx)
+        return REGK_ERR_INVALID_ARG;
+    if (ctx->pending)
+        return fail(ctx, REGK_ERR_STATE, "regk_set_stream: a batch is still pending; call regk_finish first");
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return REGK_OK;
+}
+
+int regk_set_option(regk_ctx *ctx, const char *name, int64_t value)
+{
+    if (!ctx || !name)
+        return REGK_ERR_INVALID_ARG;
+    static const char *known[] = {"async", "force_generic", "dom_cap", "json_out_cap", "skip_host_check", nullptr};
+    for (const char **k = known; *k; k++)
+        if (!strcmp(*k, name)) {
+            ctx->opt[name] = value;
+            return REGK_OK;
+        }
+    return fail(ctx, REGK_ERR_INVALID_ARG, "regk_set_option: unknown option '%s'", name);
+}
+
+int64_t regk_get_option(const regk_ctx *ctx, const char *name)
+{
+    if (!ctx || !name)
+        return -1;
+    if (!strcmp(name, "sm_count"))
+        return ctx->sm_count;
+    return opt_get(ctx, name, 0);
+}
+
+int regk_set_types(regk_ctx *ctx, const char *const *types, const uint32_t *lens, uint32_t ntypes)
+{
+    if (!ctx || (!types && ntypes))
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_set_types: NULL argument");
+    if (ntypes > 255)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_set_types: at most 255 types (type_id is one byte)");
+    if (ctx->pending)
+        return fail(ctx, REGK_ERR_STATE, "regk_set_types: a batch is still pending");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<std::string> raw(ntypes);
+    for (uint32_t i = 0; i < ntypes; i++)
+        raw[i].assign(types[i], lens ? lens[i] : strlen(types[i]));
+    std::vector<uint8_t> blob;
+    uint32_t maxq = 0;
+    std::string why;
+    const int brc = build_type_blob(raw, &blob, &maxq, &why);
+    if (brc)
+        return fail(ctx, brc == 1 ? REGK_ERR_OUT_OF_DOMAIN : REGK_ERR_INVALID_ARG, "regk_set_types: %s", why.c_str());
+    int rc = ensure_dev(ctx, ctx->blob_dev, blob.size());
+    if (rc)
+        return rc;
+    CK(cudaMemcpyAsync(ctx->blob_dev.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->types = raw;
+    ctx->blob_host = blob;
+    ctx->max_type_q = maxq;
+    return REGK_OK;
+}
+
+void *regk_host_alloc(regk_ctx *ctx, size_t bytes)
+{
+    if (!ctx)
+        return nullptr;
+    void *p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void regk_host_free(regk_ctx *ctx, void *p)
+{
+    (void)ctx;
+    if (p)
+        cudaFreeHost(p);
+}
+
+void *regk_dev_alloc(regk_ctx *ctx, size_t bytes)
+{
+    if (!ctx)
+        return nullptr;
+    void *p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void regk_dev_free(regk_ctx *ctx, void *p)
+{
+    (void)ctx;
+    if (p)
+        cudaFree(p);
+}
+
+int regk_memcpy_h2d(regk_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (!ctx)
+        return REGK_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return REGK_OK;
+}
+
+int regk_memcpy_d2h(regk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+{
+    if (!ctx)
+        return REGK_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return REGK_OK;
+}
+
+int regk_sync(regk_ctx *ctx)
+{
+    if (!ctx)
+        return REGK_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return REGK_OK;
+}
+
+int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
+{
+    if (!ctx || !b || !res)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: NULL argument");
+    if (ctx->pending)
+        return fail(ctx, REGK_ERR_STATE, "regk_register_batch: previous batch not finished (regk_finish)");
+    memset(res, 0, sizeof *res);
+    const uint64_t n = b->n;
+    const bool in_dev = b->flags & REGK_IN_DEVICE;
+    const bool out_dev = b->flags & REGK_OUT_DEVICE;
+    const bool alias = b->flags & REGK_NODE_ALIAS;
+    const bool do_path = !(b->flags & REGK_NO_PATH);
+    const bool do_json = !(b->flags & REGK_NO_JSON);
+    if (n >= (1ull << 32))
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: n must be < 2^32 per call");
+    if (do_json && ctx->types.empty())
+        return fail(ctx, REGK_ERR_STATE, "regk_register_batch: call regk_set_types first");
+    if (n && do_path && (!b->domain_off || (!b->domain_bytes && b->domain_bytes_len)))
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: domain arrays missing");
+    if (n && do_path && !alias && !b->host_off && b->host_stride == 0)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: host_off is NULL and host_stride is 0");
+    if (n && do_path && !alias && !b->host_bytes)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: host_bytes missing");
+    if (n && do_json && (!b->type_id || !b->addr_off))
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: type_id / addr_off missing");
+    if (n && do_json && b->ports_off && !b->ports && b->ports_len)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: ports missing");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+
+    /* ---- sizes of the packed arrays ---- */
+    uint64_t dom_len = b->domain_bytes_len, host_len = b->host_bytes_len, addr_len = b->addr_bytes_len,
+             ports_len = b->ports_len;
+    if (!in_dev && n) {
+        if (do_path) {
+            dom_len = b->domain_off[n];
+            host_len = alias ? 0 : (b->host_off ? b->host_off[n] : n * (uint64_t)b->host_stride);
+        }
+        if (do_json) {
+            addr_len = b->addr_off[n];
+            ports_len = b->ports_off ? b->ports_off[n] : 0;
+        }
+    } else if (in_dev && n) {
+        if (do_path && !alias && !b->host_off)
+            host_len = n * (uint64_t)b->host_stride;
+        if (do_path && dom_len == 0 && b->domain_bytes)
+            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: domain_bytes_len is required for device batches");
+        if (do_json && addr_len == 0 && b->addr_bytes)
+            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: addr_bytes_len is required for device batches");
+        if (do_json && b->ports_off && ports_len == 0 && b->ports)
+            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: ports_len is required for device batches");
+    }
+    if (alias)
+        host_len = 0;
+
+    /* ---- inputs on the device ---- */
+    const void *src[11] = {b->domain_bytes, b->domain_off, b->host_bytes, b->host_off, b->type_id, b->addr_bytes,
+        b->addr_off, b->ttl, b->ports_off, b->ports, b->ports_present};
+    const size_t sz[11] = {(size_t)dom_len, (size_t)(n + 1) * 4, (size_t)host_len, (size_t)(n + 1) * 4, (size_t)n,
+        (size_t)addr_len, (size_t)(n + 1) * 4, (size_t)n * 4, (size_t)(n + 1) * 4, (size_t)ports_len * 4, (size_t)n};
+    const bool need[11] = {do_path, do_path, do_path && !alias, do_path && !alias, do_json, do_json, do_json, do_json,
+        do_json, do_json, do_json};
+    const void *dev[11];
+    for (int i = 0; i < 11; i++) {
+        dev[i] = nullptr;
+        if (!src[i] || !need[i] || n == 0)
+            continue;
+        if (in_dev) {
+            if (((uintptr_t)src[i] & 15) != 0)
+                return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: device array %d is not 16-byte aligned", i);
+            dev[i] = src[i];
+        } else {
+            int rc = ensure_dev(ctx, ctx->in[i], sz[i] + 16);
+            if (rc)
+                return rc;
+            if (sz[i])
+                CK(cudaMemcpyAsync(ctx->in[i].p, src[i], sz[i], cudaMemcpyHostToDevice, s));
+            dev[i] = ctx->in[i].p;
+        }
+    }
+
+    /* ---- outputs (capacity = exact upper bounds) ---- */
+    const uint64_t path_cap = do_path ? dom_len + host_len + 2 * n + 16 : 16;
+    const uint64_t json_cap = do_json ? n * (uint64_t)(38 + 2 * ctx->max_type_q + 4 + 18 + 11) + 2 * addr_len +
+        11 * ports_len + 16 : 16;
+    int rc;
+    if ((rc = ensure_dev(ctx, ctx->path_bytes, path_cap)) || (rc = ensure_dev(ctx, ctx->path_off, (n + 1) * 8)) ||
+        (rc = ensure_dev(ctx, ctx->json_bytes, json_cap)) || (rc = ensure_dev(ctx, ctx->json_off, (n + 1) * 8)))
+        return rc;
+
+    /* ---- workspace ---- */
+    const uint64_t ntiles = (n + TILE - 1) / TILE;
+    const size_t status_off = 0, ticket_off = 64, tiles_off = 128;
+    const size_t work_bytes = tiles_off + 2 * ntiles * 8 + 64;
+    if ((rc = ensure_dev(ctx, ctx->work, work_bytes)))
+        return rc;
+    uint8_t *wk = (uint8_t *)ctx->work.p;
+    CK(cudaMemsetAsync(wk, 0, work_bytes, s));
+    DevStatus *d_status = (DevStatus *)(wk + status_off);
+    uint32_t *tickets = (uint32_t *)(wk + ticket_off);
+    unsigned long long *tiles_p = (unsigned long long *)(wk + tiles_off);
+    unsigned long long *tiles_j = tiles_p + ntiles;
+
+    if (n == 0) {
+        CK(cudaMemsetAsync(ctx->path_off.p, 0, 8, s));
+        CK(cudaMemsetAsync(ctx->json_off.p, 0, 8, s));
+    }
+    uint32_t launches = 0;
+    const uint32_t force_generic = (uint32_t)opt_get(ctx, "force_generic", 0);
+    CK(cudaEventRecord(ctx->ev[0], s));
+    if (n && do_path) {
+        PathParams p{};
+        p.n = n;
+        p.domain_bytes = (const uint8_t *)dev[0];
+        p.domain_off = (const uint32_t *)dev[1];
+        p.host_bytes = (const uint8_t *)dev[2];
+        p.host_off = (const uint32_t *)dev[3];
+        p.host_stride = b->host_stride;
+        p.out_bytes = (uint8_t *)ctx->path_bytes.p;
+        p.out_off = (unsigned long long *)ctx->path_off.p;
+        p.out_capacity = path_cap;
+        p.scan.tile_status = tiles_p;
+        p.scan.ticket = tickets + 0;
+        p.scan.base_in = nullptr;
+        p.status = d_status;
+        p.force_generic = force_generic;
+        /* shared-memory budget: twice the mean tile, clamped; tiles that do not fit go generic */
+        const uint64_t mean_dom_tile = dom_len / std::max<uint64_t>(ntiles, 1) + 1;
+        uint32_t dom_cap = (uint32_t)opt_get(ctx, "dom_cap", 0);
+        if (!dom_cap)
+            dom_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(align16(mean_dom_tile * 3 / 2 + 512), 4096), 49152);
+        dom_cap = (uint32_t)align16(dom_cap);
+        uint32_t host_cap = 0;
+        if (!alias) {
+            const uint64_t mean_host_tile = p.host_off ? host_len / std::max<uint64_t>(ntiles, 1) + 1
+                                                       : (uint64_t)TILE * b->host_stride;
+            host_cap = (uint32_t)std::min<uint64_t>(align16((p.host_off ? mean_host_tile * 3 / 2 + 512 : mean_host_tile) + 16), 49152);
+        }
+        uint32_t out_cap = (uint32_t)align16((uint64_t)dom_cap + host_cap + 2 * TILE + 32);
+        size_t smem = (size_t)dom_cap + 32 + (alias ? 0 : host_cap + 32) + out_cap + 32;
+        if (smem > (size_t)ctx->max_smem_optin)
+            return fail(ctx, REGK_ERR_INVALID_ARG, "path kernel needs %zu B of shared memory (> %d)", smem, ctx->max_smem_optin);
+        p.dom_cap = dom_cap;
+        p.host_cap = host_cap;
+        p.out_cap = out_cap;
+        if (alias) {
+            CK(cudaFuncSetAttribute(regk_path_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            regk_path_kernel<true><<<(unsigned)ntiles, TILE, smem, s>>>(p);
+        } else {
+            CK(cudaFuncSetAttribute(regk_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            regk_path_kernel<false><<<(unsigned)ntiles, TILE, smem, s>>>(p);
+        }
+        CK(cudaGetLastError());
+        launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[1], s));
+    if (n && do_json) {
+        JsonParams p{};
+        p.n = n;
+        p.type_id = (const uint8_t *)dev[4];
+        p.addr_bytes = (const uint8_t *)dev[5];
+        p.addr_off = (const uint32_t *)dev[6];
+        p.ttl = (const int32_t *)dev[7];
+        p.ports_off = (const uint32_t *)dev[8];
+        p.ports = (const uint32_t *)dev[9];
+        p.ports_present = (const uint8_t *)dev[10];
+        p.frag_blob = (const uint8_t *)ctx->blob_dev.p;
+        p.ntypes = (uint32_t)ctx->types.size();
+        p.blob_bytes = (uint32_t)ctx->blob_host.size();
+        p.out_bytes = (uint8_t *)ctx->json_bytes.p;
+        p.out_off = (unsigned long long *)ctx->json_off.p;
+        p.out_capacity = json_cap;
+        p.scan.tile_status = tiles_j;
+        p.scan.ticket = tickets + 1;
+        p.scan.base_in = nullptr;
+        p.status = d_status;
+        p.force_generic = force_generic;
+        uint32_t out_cap = (uint32_t)opt_get(ctx, "json_out_cap", 0);
+        if (!out_cap) {
+            /* mean payload estimate: fixed keys + type twice + address twice + ttl + ports */
+            const uint64_t mean = 42 + 2ull * ctx->max_type_q + (n ? 2 * addr_len / n : 0) + 11 +
+                (ports_len ? 11 + (n ? 6 * ports_len / n : 0) : 0) + 2;
+            out_cap = (uint32_t)std::min<uint64_t>(align16(mean * TILE * 5 / 4 + 1024), 98304);
+        }
+        out_cap = (uint32_t)align16(out_cap);
+        p.out_cap = out_cap;
+        size_t smem = (size_t)p.blob_bytes + out_cap + 32;
+        if (smem > (size_t)ctx->max_smem_optin)
+            return fail(ctx, REGK_ERR_INVALID_ARG, "json kernel needs %zu B of shared memory (> %d)", smem, ctx->max_smem_optin);
+        CK(cudaFuncSetAttribute(regk_json_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        regk_json_kernel<<<(unsigned)ntiles, TILE, smem, s>>>(p);
+        CK(cudaGetLastError());
+        launches++;
+    }
+    CK(cudaEventRecord(ctx->ev[2], s));
+    CK(cudaMemcpyAsync(ctx->h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+
+    ctx->pending = true;
+    ctx->pend_n = n;
+    ctx->pend_flags = b->flags;
+    ctx->pend_launches = launches;
+    res->n = n;
+    res->flags = out_dev ? REGK_OUT_DEVICE : 0;
+    res->launches = launches;
+    res->opaque = ctx;
+    if (opt_get(ctx, "async", 0))
+        return REGK_OK;
+    return regk_finish(ctx, res);
+}
+
+int regk_finish(regk_ctx *ctx, regk_result *res)
+{
+    if (!ctx || !res)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_finish: NULL argument");
+    if (!ctx->pending)
+        return fail(ctx, REGK_ERR_STATE, "regk_finish: nothing pending");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    cudaError_t e = cudaStreamSynchronize(s);
+    ctx->pending = false;
+    if (e != cudaSuccess)
+        return fail(ctx, REGK_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
+    const DevStatus st = *ctx->h_status;
+    const uint64_t n = ctx->pend_n;
+    const bool out_dev = ctx->pend_flags & REGK_OUT_DEVICE;
+    float ms_p = 0, ms_j = 0;
+    cudaEventElapsedTime(&ms_p, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ms_j, ctx->ev[1], ctx->ev[2]);
+    res->n = n;
+    res->path_kernel_ms = ms_p;
+    res->json_kernel_ms = ms_j;
+    res->kernel_ms = ms_p + ms_j;
+    res->launches = ctx->pend_launches;
+    res->bad_bits = st.bad_bits;
+    res->first_bad = st.bad_bits ? ~st.first_bad : 0;
+    res->path_total = st.path_total;
+    res->json_total = st.json_total;
+    if (st.overflow)
+        return fail(ctx, REGK_ERR_CUDA, "internal error: output capacity bound exceeded");
+    if (st.bad_bits) {
+        res->path_total = res->json_total = 0;
+        return fail(ctx, REGK_ERR_OUT_OF_DOMAIN,
+            "record %llu is outside the supported input domain (REGK_BAD bits 0x%x); no output produced",
+            (unsigned long long)res->first_bad, st.bad_bits);
+    }
+    if (out_dev) {
+        res->flags = REGK_OUT_DEVICE;
+        res->path_bytes = (uint8_t *)ctx->path_bytes.p;
+        res->path_off = (uint64_t *)ctx->path_off.p;
+        res->json_bytes = (uint8_t *)ctx->json_bytes.p;
+        res->json_off = (uint64_t *)ctx->json_off.p;
+        return REGK_OK;
+    }
+    int rc;
+    const bool do_path = !(ctx->pend_flags & REGK_NO_PATH), do_json = !(ctx->pend_flags & REGK_NO_JSON);
+    if ((rc = ensure_host(ctx, ctx->h_path_bytes, st.path_total + 16)) || (rc = ensure_host(ctx, ctx->h_path_off, (n + 1) * 8)) ||
+        (rc = ensure_host(ctx, ctx->h_json_bytes, st.json_total + 16)) || (rc = ensure_host(ctx, ctx->h_json_off, (n + 1) * 8)))
+        return rc;
+    if (n && do_path) {
+        CK(cudaMemcpyAsync(ctx->h_path_bytes.p, ctx->path_bytes.p, st.path_total, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_path_off.p, ctx->path_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    } else {
+        memset(ctx->h_path_off.p, 0, (n + 1) * 8);
+    }
+    if (n && do_json) {
+        CK(cudaMemcpyAsync(ctx->h_json_bytes.p, ctx->json_bytes.p, st.json_total, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_json_off.p, ctx->json_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    } else {
+        memset(ctx->h_json_off.p, 0, (n + 1) * 8);
+    }
+    CK(cudaStreamSynchronize(s));
+    res->flags = 0;
+    res->path_bytes = (uint8_t *)ctx->h_path_bytes.p;
+    res->path_off = (uint64_t *)ctx->h_path_off.p;
+    res->json_bytes = (uint8_t *)ctx->h_json_bytes.p;
+    res->json_off = (uint64_t *)ctx->h_json_off.p;
+    return REGK_OK;
+}
+
+int regk_release(regk_ctx *ctx, regk_result *res)
+{
+    if (!ctx || !res)
+        return REGK_ERR_INVALID_ARG;
+    /* single-slot ownership: buffers are recycled by the next batch; nothing to free eagerly */
+    res->path_bytes = res->json_bytes = nullptr;
+    res->path_off = res->json_off = nullptr;
+    res->opaque = nullptr;
+    return REGK_OK;
+}
+
+}  /* extern "C" */

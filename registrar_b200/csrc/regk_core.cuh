@@ -1,0 +1,553 @@
+/*
+ * regk_core.cuh — per-record composers of the registration hot path, written
+ * as word-at-a-time (SWAR) byte manipulation so that one GPU thread can turn
+ * one service record into its znode path and its JSON payload with a few
+ * hundred integer instructions and 32-bit shared-memory accesses.
+ *
+ * Reference semantics restated here (relative to /root/reference):
+ *   A1  lib/register.js:34-39   domainToPath(): lower-case, split on '.',
+ *                               reverse, join with '/', leading '/'
+ *   A2  lib/register.js:221-223 path.join(p, os.hostname()): posix normalise
+ *                               (empty labels vanish), '/' + hostname appended
+ *   A3  lib/register.js:141-155 host-record object, key order type, address,
+ *                               ttl, <type>:{address, ports}
+ *   A4  lib/register.js:159     zkplus JSON.stringify -> compact JSON bytes
+ *
+ * Everything is templated on a word source (where the record's input bytes
+ * live) and a byte sink (where output bytes go) so the same code serves the
+ * shared-memory fast path, the direct-to-global generic path, and the CPU
+ * logic tests in tests/ (RG_HD expands to nothing under a host compiler).
+ */
+#ifndef REGK_CORE_CUH
+#define REGK_CORE_CUH
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RG_HD __host__ __device__ __forceinline__
+#define RG_D __device__ __forceinline__
+#else
+#define RG_HD inline
+#define RG_D inline
+#endif
+
+namespace regk {
+
+/* validation bits: keep in sync with include/regk.h */
+enum : uint32_t {
+    BAD_DOMAIN_BYTE = 1u << 0,
+    BAD_HOST_BYTE = 1u << 1,
+    BAD_ADDR_BYTE = 1u << 2,
+    BAD_TYPE_ID = 1u << 3,
+    BAD_TOO_LARGE = 1u << 4,
+};
+
+/* ---------------------------------------------------------------- SWAR -- */
+
+RG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t shift_bits)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, shift_bits);          /* shift_bits in [0, 31] */
+#else
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (shift_bits & 31));
+#endif
+}
+
+RG_HD uint32_t popc32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popc(v);
+#else
+    return (uint32_t)__builtin_popcount(v);
+#endif
+}
+
+RG_HD uint32_t clz32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz((int)v);
+#else
+    return v ? (uint32_t)__builtin_clz(v) : 32u;
+#endif
+}
+
+/* mask with the low n bytes set, n in [0, 4] */
+RG_HD uint32_t low_bytes(uint32_t n)
+{
+    return n >= 4 ? 0xFFFFFFFFu : ((1u << (8 * n)) - 1u);
+}
+
+/* For a word of 7-bit bytes: bit 7 of every byte that equals c (exact per byte). */
+RG_HD uint32_t eq7(uint32_t v7, uint32_t c)
+{
+    uint32_t x = v7 ^ (c * 0x01010101u);                 /* 0 where equal, still 7-bit */
+    return ~(x + 0x7F7F7F7Fu) & 0x80808080u;             /* no inter-byte carry for 7-bit bytes */
+}
+
+/* For a word of 7-bit bytes: bit 7 of every byte that is zero after masking with m. */
+RG_HD uint32_t zero7(uint32_t v7)
+{
+    return ~(v7 + 0x7F7F7F7Fu) & 0x80808080u;
+}
+
+/* ASCII lower-casing of 4 bytes (7-bit bytes): 'A'..'Z' -> 'a'..'z'  (String.prototype.toLowerCase
+ * restricted to ASCII, lib/register.js:38). */
+RG_HD uint32_t lower7(uint32_t v7)
+{
+    uint32_t ge_A = v7 + 0x3F3F3F3Fu;                    /* bit7 iff byte >= 0x41 */
+    uint32_t gt_Z = v7 + 0x25252525u;                    /* bit7 iff byte >= 0x5B */
+    uint32_t up = ge_A & ~gt_Z & 0x80808080u;
+    return v7 | (up >> 2);                               /* + 0x20 */
+}
+
+/* ---------------------------------------------------------------- sinks -- */
+
+/*
+ * WordSink: sequential byte writer into a 32-bit-word buffer (shared memory on
+ * the GPU).  Bytes are accumulated in a 64-bit shift register and stored as
+ * aligned words; only the first and the last word of a record, which are shared
+ * with the neighbouring records, are written byte by byte.
+ */
+struct WordSink {
+    uint32_t *words;        /* buffer base (word aligned) */
+    uint32_t wi;            /* index of the word the low bytes of acc belong to */
+    uint32_t nb;            /* bytes pending in acc, including the `head` foreign bytes */
+    uint32_t head;          /* low bytes of the first word that belong to the previous record */
+    uint64_t acc;
+
+    RG_HD void init(uint32_t *base, uint32_t byte_off)
+    {
+        words = base;
+        wi = byte_off >> 2;
+        head = byte_off & 3u;
+        nb = head;
+        acc = 0;
+    }
+    RG_HD void flush_word()
+    {
+        uint32_t w = (uint32_t)acc;
+        if (head) {
+            uint8_t *b = reinterpret_cast<uint8_t *>(words + wi);
+            for (uint32_t k = head; k < 4; k++)
+                b[k] = (uint8_t)(w >> (8 * k));
+            head = 0;
+        } else {
+            words[wi] = w;
+        }
+        wi++;
+        acc >>= 32;
+        nb -= 4;
+    }
+    /* append the low n bytes of v (1 <= n <= 4); bytes of v above n must be zero */
+    RG_HD void put(uint32_t v, uint32_t n)
+    {
+        acc |= (uint64_t)v << (8 * nb);
+        nb += n;
+        if (nb >= 4)
+            flush_word();
+    }
+    RG_HD void put4(uint32_t v)
+    {
+        acc |= (uint64_t)v << (8 * nb);
+        nb += 4;
+        flush_word();
+    }
+    RG_HD void put1(uint32_t c)
+    {
+        put(c, 1);
+    }
+    RG_HD void finish()
+    {
+        uint8_t *b = reinterpret_cast<uint8_t *>(words + wi);
+        for (uint32_t k = head; k < nb; k++)
+            b[k] = (uint8_t)(acc >> (8 * k));
+        head = 0;
+        nb = 0;
+    }
+};
+
+/* ByteSink: same interface, writes straight to a byte pointer (generic path / CPU tests). */
+struct ByteSink {
+    uint8_t *p;
+    RG_HD void init(uint8_t *dst) { p = dst; }
+    RG_HD void put(uint32_t v, uint32_t n)
+    {
+        for (uint32_t k = 0; k < n; k++)
+            *p++ = (uint8_t)(v >> (8 * k));
+    }
+    RG_HD void put4(uint32_t v) { put(v, 4); }
+    RG_HD void put1(uint32_t c) { *p++ = (uint8_t)c; }
+    RG_HD void finish() {}
+};
+
+/* CountSink: length only. */
+struct CountSink {
+    uint32_t n;
+    RG_HD void init() { n = 0; }
+    RG_HD void put(uint32_t, uint32_t k) { n += k; }
+    RG_HD void put4(uint32_t) { n += 4; }
+    RG_HD void put1(uint32_t) { n += 1; }
+    RG_HD void finish() {}
+};
+
+/* -------------------------------------------------------------- sources -- */
+
+/* Word source over an aligned 32-bit buffer that is readable one word past the
+ * last byte used (shared-memory staging buffers are padded accordingly). */
+struct PaddedWords {
+    const uint32_t *w;
+    RG_HD uint32_t word(uint32_t i) const { return w[i]; }
+    RG_HD uint32_t word_hi(uint32_t i, uint32_t /*needed*/) const { return w[i]; }
+};
+
+/* Word source over global memory: never touches a word that holds no needed byte. */
+struct GuardedWords {
+    const uint32_t *w;
+    RG_HD uint32_t word(uint32_t i) const { return w[i]; }
+    RG_HD uint32_t word_hi(uint32_t i, uint32_t needed) const { return needed ? w[i] : 0u; }
+};
+
+/*
+ * Copy len bytes starting at byte offset `off` of `src` into `sink`, optionally
+ * lower-casing, and OR the raw bytes into *seen (for validation).  One source
+ * word load and one sink word per 4 bytes.
+ */
+template <bool LOWER, class Src, class Sink>
+RG_HD void copy_bytes(const Src &src, uint32_t off, uint32_t len, Sink &sink)
+{
+    if (len == 0)
+        return;
+    uint32_t wi = off >> 2;
+    const uint32_t sh = (off & 3u) * 8u;
+    uint32_t lo = src.word(wi);
+    while (len >= 4) {
+        /* the next word is needed iff the 4 bytes straddle it */
+        uint32_t hi = src.word_hi(wi + 1, sh != 0 || len > 4);
+        uint32_t v = funnel_r(lo, hi, sh);
+        if (LOWER)
+            v = lower7(v & 0x7F7F7F7Fu);
+        sink.put4(v);
+        lo = hi;
+        wi++;
+        len -= 4;
+    }
+    if (len) {
+        uint32_t hi = src.word_hi(wi + 1, sh + 8 * len > 32);
+        uint32_t v = funnel_r(lo, hi, sh) & low_bytes(len);
+        if (LOWER)
+            v = lower7(v & 0x7F7F7F7Fu);
+        sink.put(v, len);
+    }
+}
+
+/* ------------------------------------------------------ A1/A2: the path -- */
+
+struct DomainStats {
+    uint32_t nondot;        /* bytes that are not '.' */
+    uint32_t labels;        /* non-empty labels */
+    uint32_t bad;           /* REGK_BAD_DOMAIN_BYTE or 0 */
+};
+
+/*
+ * One forward pass over the domain (bytes [off, off+L) of src): counts what the
+ * path length needs and applies the input fence (byte >= 0x80 or '/').
+ */
+template <class Src>
+RG_HD DomainStats scan_domain(const Src &src, uint32_t off, uint32_t L)
+{
+    DomainStats st;
+    st.nondot = 0;
+    st.labels = 0;
+    st.bad = 0;
+    if (L == 0)
+        return st;
+    uint32_t wi = off >> 2;
+    const uint32_t sh = (off & 3u) * 8u;
+    uint32_t lo = src.word(wi);
+    uint32_t prev_dot = 0x80u;          /* position -1 counts as a separator */
+    uint32_t hibits = 0, slash = 0;
+    uint32_t rem = L;
+    while (rem) {
+        uint32_t nbytes = rem < 4 ? rem : 4;
+        uint32_t hi = src.word_hi(wi + 1, sh + 8 * nbytes > 32 || rem > 4);
+        uint32_t v = funnel_r(lo, hi, sh);
+        uint32_t keep = low_bytes(nbytes);
+        v &= keep;
+        hibits |= v;
+        uint32_t v7 = v & 0x7F7F7F7Fu;
+        uint32_t x = v7 ^ 0x2E2E2E2Eu;                      /* '.' -> 0x00, '/' -> 0x01 */
+        uint32_t dot = zero7(x);
+        uint32_t dot_or_slash = zero7(x & 0x7E7E7E7Eu);
+        slash |= (dot ^ dot_or_slash) & (keep & 0x80808080u);
+        uint32_t valid7 = keep & 0x80808080u;
+        uint32_t nd = ~dot & valid7;                        /* non-dot bytes inside the domain */
+        uint32_t before = (dot << 8) | prev_dot;            /* bit7 of byte k set iff byte k-1 is a separator */
+        st.nondot += popc32(nd);
+        st.labels += popc32(nd & before);
+        prev_dot = dot >> 24;
+        lo = hi;
+        wi++;
+        rem -= nbytes;
+    }
+    if ((hibits & 0x80808080u) || slash)
+        st.bad = BAD_DOMAIN_BYTE;
+    return st;
+}
+
+/* Absolute byte position of the last '.' in [a, e) of src, or a - 1 when there is none (e > a). */
+template <class Src>
+RG_HD int32_t find_prev_dot(const Src &src, uint32_t a, uint32_t e)
+{
+    uint32_t wi = (e - 1) >> 2;
+    uint32_t nkeep = e - 4 * wi;                            /* 1..4 bytes of this word are below e */
+    uint32_t dm = eq7(src.word(wi) & 0x7F7F7F7Fu, 0x2E) & low_bytes(nkeep);
+    for (;;) {
+        if (dm) {
+            int32_t pos = (int32_t)(4 * wi + ((31u - clz32(dm)) >> 3));
+            return pos >= (int32_t)a ? pos : (int32_t)a - 1;
+        }
+        if (4 * wi <= a)
+            return (int32_t)a - 1;
+        wi--;
+        dm = eq7(src.word(wi) & 0x7F7F7F7Fu, 0x2E);
+    }
+}
+
+/*
+ * Emit the znode path of one record.
+ *   ALIAS = false: host node, path.join(domainToPath(domain), hostname) (A2):
+ *                  '/' + each non-empty label from last to first + '/' ... + '/' + hostname
+ *   ALIAS = true : alias node, domainToPath(domain) un-normalised (A1): every label,
+ *                  empty ones included, preceded by '/'
+ * dom: bytes [doff, doff+L) of dsrc; host: bytes [hoff, hoff+H) of hsrc.
+ */
+template <bool ALIAS, class DSrc, class HSrc, class Sink>
+RG_HD void emit_path(const DSrc &dsrc, uint32_t doff, uint32_t L, const HSrc &hsrc, uint32_t hoff,
+    uint32_t H, Sink &sink)
+{
+    uint32_t e = doff + L;                                  /* end (exclusive) of the current label */
+    for (;;) {
+        int32_t dot = e > doff ? find_prev_dot(dsrc, doff, e) : (int32_t)doff - 1;
+        uint32_t s = (uint32_t)(dot + 1);
+        if (ALIAS || e > s) {
+            sink.put1('/');
+            copy_bytes<true>(dsrc, s, e - s, sink);
+        }
+        if (s == doff)
+            break;
+        e = s - 1;
+    }
+    if (!ALIAS) {
+        sink.put1('/');
+        copy_bytes<false>(hsrc, hoff, H, sink);
+    }
+}
+
+RG_HD uint32_t path_length(const DomainStats &st, uint32_t L, uint32_t H, bool alias)
+{
+    return alias ? L + 1 : 1 + st.nondot + st.labels + H;
+}
+
+/* Hostname fence: non-empty, not "." / "..", bytes in 0x01..0x7f except '/'. */
+template <class Src>
+RG_HD uint32_t check_host(const Src &src, uint32_t off, uint32_t H)
+{
+    if (H == 0)
+        return BAD_HOST_BYTE;
+    uint32_t wi = off >> 2;
+    const uint32_t sh = (off & 3u) * 8u;
+    uint32_t lo = src.word(wi);
+    uint32_t hibits = 0, hit = 0, first = 0;
+    uint32_t rem = H;
+    bool is_first = true;
+    while (rem) {
+        uint32_t nbytes = rem < 4 ? rem : 4;
+        uint32_t hi = src.word_hi(wi + 1, sh + 8 * nbytes > 32 || rem > 4);
+        uint32_t keep = low_bytes(nbytes);
+        uint32_t v = funnel_r(lo, hi, sh) & keep;
+        if (is_first) {
+            first = v;
+            is_first = false;
+        }
+        hibits |= v;
+        uint32_t v7 = v & 0x7F7F7F7Fu;
+        hit |= (eq7(v7, 0x2F) | zero7(v7)) & keep;          /* '/' or NUL */
+        lo = hi;
+        wi++;
+        rem -= nbytes;
+    }
+    bool dots = (H == 1 && first == 0x2Eu) || (H == 2 && first == 0x2E2Eu);
+    return ((hibits & 0x80808080u) || hit || dots) ? (uint32_t)BAD_HOST_BYTE : 0u;
+}
+
+/* --------------------------------------------------- A3/A4: the payload -- */
+
+/* Decimal digits of r < 10000 as 4 ASCII bytes, most significant digit in byte 0. */
+RG_HD uint32_t dec4(uint32_t r)
+{
+    uint32_t hi = (r * 5243u) >> 19;                        /* r / 100 for r < 10000 */
+    uint32_t lo = r - hi * 100u;
+    uint32_t pair = hi | (lo << 16);                        /* two values < 100 in 16-bit lanes */
+    uint32_t tens = ((pair * 103u) >> 10) & 0x000F000Fu;    /* x / 10 for x < 100, per lane */
+    uint32_t ones = pair - tens * 10u;
+    return (tens | (ones << 8)) + 0x30303030u;
+}
+
+RG_HD uint32_t ndigits4(uint32_t r)                          /* r < 10000 */
+{
+    return 1u + (r >= 10u) + (r >= 100u) + (r >= 1000u);
+}
+
+RG_HD uint32_t ndigits_u32(uint32_t v)
+{
+    if (v < 10000u)
+        return ndigits4(v);
+    if (v < 100000000u)
+        return 4u + ndigits4(v / 10000u);
+    return 8u + ndigits4(v / 100000000u);
+}
+
+/* Number::toString for an unsigned 32-bit integer (ports, |ttl|). */
+template <class Sink>
+RG_HD void put_u32_dec(uint32_t v, Sink &sink)
+{
+    if (v < 10000u) {
+        uint32_t n = ndigits4(v);
+        sink.put(dec4(v) >> (8 * (4 - n)), n);
+        return;
+    }
+    uint32_t q = v / 10000u, r = v - q * 10000u;
+    if (q < 10000u) {
+        uint32_t n = ndigits4(q);
+        sink.put(dec4(q) >> (8 * (4 - n)), n);
+    } else {
+        uint32_t q2 = q / 10000u, r2 = q - q2 * 10000u;     /* q2 <= 42 */
+        uint32_t n = ndigits4(q2);
+        sink.put(dec4(q2) >> (8 * (4 - n)), n);
+        sink.put4(dec4(r2));
+    }
+    sink.put4(dec4(r));
+}
+
+RG_HD uint32_t ndigits_i32(int32_t v)
+{
+    uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+    return ndigits_u32(u) + (v < 0 ? 1u : 0u);
+}
+
+template <class Sink>
+RG_HD void put_i32_dec(int32_t v, Sink &sink)
+{
+    uint32_t u = (uint32_t)v;
+    if (v < 0) {
+        sink.put1('-');
+        u = 0u - u;
+    }
+    put_u32_dec(u, sink);
+}
+
+/* Address fence on a word of address bytes (masked to its valid bytes): every byte
+ * must be in 0x20..0x7f and must not be '"' or '\' (they would need a JSON escape). */
+RG_HD uint32_t addr_word_bad(uint32_t v, uint32_t keep)
+{
+    uint32_t v7 = v & 0x7F7F7F7Fu;
+    uint32_t ctl = zero7(v7 & 0x60606060u);                 /* byte < 0x20 */
+    uint32_t q = eq7(v7, 0x22) | eq7(v7, 0x5C);
+    return ((v & 0x80808080u) | ((ctl | q) & keep)) != 0;
+}
+
+/*
+ * Per-type fragment table (built on the host by regk_set_types, JSON escaping
+ * already applied).  For type T:
+ *   f1 = {"type":"T","address":"        f2 = ,"T":{"address":"
+ * Fragments start on word boundaries inside `blob`.
+ */
+struct TypeFrag {
+    uint16_t f1_off, f1_len, f2_off, f2_len;                /* byte offsets into the blob */
+};
+
+template <class Src, class Sink>
+RG_HD void put_aligned(const Src &blob, uint32_t off, uint32_t len, Sink &sink)
+{
+    uint32_t wi = off >> 2;
+    while (len >= 4) {
+        sink.put4(blob.word(wi++));
+        len -= 4;
+    }
+    if (len)
+        sink.put(blob.word(wi) & low_bytes(len), len);
+}
+
+RG_HD uint32_t json_length(uint32_t f1_len, uint32_t f2_len, uint32_t al, bool has_ttl, int32_t ttl,
+    bool has_ports, uint32_t k, uint32_t port_digits)
+{
+    /* f1 + A + ('"' | '","ttl":' + ttl) + f2 + A + ('"}}' | '","ports":[' ... ']}}') */
+    uint32_t n = f1_len + f2_len + 2 * al + 4;
+    if (has_ttl)
+        n += 7 + ndigits_i32(ttl);
+    if (has_ports)
+        n += 11 + port_digits + (k ? k - 1 : 0);
+    return n;
+}
+
+#define RG_LE4(a, b, c, d) ((uint32_t)(uint8_t)(a) | ((uint32_t)(uint8_t)(b) << 8) | \
+    ((uint32_t)(uint8_t)(c) << 16) | ((uint32_t)(uint8_t)(d) << 24))
+
+/* the first (up to) 16 address bytes, from registers */
+template <class Sink>
+RG_HD void put_addr16(const uint32_t (&aw)[4], uint32_t n, Sink &sink)
+{
+    #pragma unroll
+    for (int w = 0; w < 4; w++) {
+        if (n >= 4u * (w + 1))
+            sink.put4(aw[w]);
+        else if (n > 4u * w)
+            sink.put(aw[w] & low_bytes(n - 4u * w), n - 4u * w);
+    }
+}
+
+/*
+ * Emit the JSON payload of one host record (A3 + A4):
+ *   {"type":"T","address":"A"[,"ttl":N],"T":{"address":"A"[,"ports":[p,...]]}}
+ * The address is passed as up to 16 bytes in registers (aw[0..3]); a longer
+ * address continues from asrc at byte offset aoff + 16.  ports are read
+ * through port(i).
+ */
+template <class FSrc, class ASrc, class PortFn, class Sink>
+RG_HD void emit_json(const FSrc &blob, const TypeFrag &tf, const uint32_t (&aw)[4], const ASrc &asrc,
+    uint32_t aoff, uint32_t al, bool has_ttl, int32_t ttl, bool has_ports, uint32_t k, PortFn port,
+    Sink &sink)
+{
+    const uint32_t a16 = al < 16u ? al : 16u;
+    put_aligned(blob, tf.f1_off, tf.f1_len, sink);          /* {"type":"T","address":" */
+    put_addr16(aw, a16, sink);
+    if (al > 16u)
+        copy_bytes<false>(asrc, aoff + 16u, al - 16u, sink);
+    if (has_ttl) {
+        sink.put4(RG_LE4('"', ',', '"', 't'));              /* ","ttl": */
+        sink.put4(RG_LE4('t', 'l', '"', ':'));
+        put_i32_dec(ttl, sink);
+    } else {
+        sink.put1('"');
+    }
+    put_aligned(blob, tf.f2_off, tf.f2_len, sink);          /* ,"T":{"address":" */
+    put_addr16(aw, a16, sink);
+    if (al > 16u)
+        copy_bytes<false>(asrc, aoff + 16u, al - 16u, sink);
+    if (has_ports) {
+        sink.put4(RG_LE4('"', ',', '"', 'p'));              /* ","ports":[ */
+        sink.put4(RG_LE4('o', 'r', 't', 's'));
+        sink.put(RG_LE4('"', ':', '[', 0), 3);
+        for (uint32_t i = 0; i < k; i++) {
+            if (i)
+                sink.put1(',');
+            put_u32_dec(port(i), sink);
+        }
+        sink.put(RG_LE4(']', '}', '}', 0), 3);
+    } else {
+        sink.put(RG_LE4('"', '}', '}', 0), 3);
+    }
+}
+
+}  /* namespace regk */
+#endif /* REGK_CORE_CUH */

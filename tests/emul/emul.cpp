@@ -1,0 +1,263 @@
+/*
+ * emul.cpp — TEST INFRASTRUCTURE: host-compiled harness around the device
+ * composers of registrar_b200/csrc/regk_core.cuh.
+ *
+ * There is no GPU in the build container, so the word-wise (SWAR) logic that the
+ * kernels run per thread is exercised here under g++ on the same inputs the
+ * oracle sees: the staging layout (16-byte phase of the tile in the packed
+ * stream), the shared-word WordSink protocol between neighbouring records, the
+ * length formulas and the fence.  It mirrors the per-tile control flow of
+ * regk_kernels.cuh with a serial scan in place of the look-back.  Built and
+ * used only by tests/test_core_emul.py; it is not part of the product library.
+ */
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/regk.h"
+#include "../../registrar_b200/csrc/regk_core.cuh"
+
+using namespace regk;
+
+namespace {
+constexpr uint32_t TILE = 256;
+
+struct Frags {
+    std::vector<uint8_t> blob;
+};
+}
+
+extern "C" {
+
+/* returns OR of bad bits; outputs must be large enough (caller sizes from the oracle) */
+uint32_t emul_paths(const regk_batch *b, int generic, uint8_t *out_bytes, uint64_t *out_off, uint64_t *first_bad)
+{
+    const bool alias = b->flags & REGK_NODE_ALIAS;
+    const uint64_t n = b->n;
+    uint32_t bad_all = 0;
+    uint64_t fb = UINT64_MAX;
+    uint64_t base = 0;
+    for (uint64_t r0 = 0; r0 < n; r0 += TILE) {
+        const uint32_t nrec = (uint32_t)std::min<uint64_t>(TILE, n - r0);
+        const uint64_t D0 = b->domain_off[r0], D1 = b->domain_off[r0 + nrec];
+        const uint64_t HB0 = alias ? 0 : (b->host_off ? b->host_off[r0] : r0 * b->host_stride);
+        const uint64_t HB1 = alias ? 0 : (b->host_off ? b->host_off[r0 + nrec] : (r0 + nrec) * b->host_stride);
+        const uint64_t da0 = D0 & ~15ull, ha0 = HB0 & ~15ull;
+        /* staged images, poisoned outside the tile's own bytes */
+        std::vector<uint32_t> sdom((D1 - da0) / 4 + 16, 0xA5A5A5A5u), shost((HB1 - ha0) / 4 + 16, 0x5A5A5A5Au);
+        if (D1 > da0)
+            memcpy(sdom.data(), b->domain_bytes + da0, D1 - da0);
+        if (HB1 > ha0)
+            memcpy(shost.data(), b->host_bytes + ha0, HB1 - ha0);
+        std::vector<uint32_t> len(nrec), local(nrec);
+        std::vector<DomainStats> st(nrec);
+        uint32_t total = 0;
+        for (uint32_t t = 0; t < nrec; t++) {
+            const uint64_t r = r0 + t;
+            const uint32_t d0 = b->domain_off[r], L = b->domain_off[r + 1] - d0;
+            const uint64_t h0 = alias ? 0 : (b->host_off ? b->host_off[r] : r * b->host_stride);
+            const uint32_t H = alias ? 0 : (b->host_off ? b->host_off[r + 1] - b->host_off[r] : b->host_stride);
+            uint32_t bad;
+            if (generic) {
+                GuardedWords ds{(const uint32_t *)b->domain_bytes}, hs{(const uint32_t *)b->host_bytes};
+                st[t] = scan_domain(ds, d0, L);
+                bad = st[t].bad | (alias ? 0 : check_host(hs, (uint32_t)h0, H));
+            } else {
+                PaddedWords ds{sdom.data()}, hs{shost.data()};
+                st[t] = scan_domain(ds, (uint32_t)(d0 - da0), L);
+                bad = st[t].bad | (alias ? 0 : check_host(hs, (uint32_t)(h0 - ha0), H));
+            }
+            if (bad) {
+                bad_all |= bad;
+                fb = std::min<uint64_t>(fb, r);
+            }
+            len[t] = path_length(st[t], L, H, alias);
+            local[t] = total;
+            total += len[t];
+        }
+        const uint32_t shift = (uint32_t)(base & 15);
+        std::vector<uint32_t> sout((shift + total) / 4 + 16, 0xEEEEEEEEu);
+        /* compose in reverse thread order: neighbours must not clobber shared words */
+        for (uint32_t tt = nrec; tt-- > 0;) {
+            const uint64_t r = r0 + tt;
+            const uint32_t d0 = b->domain_off[r], L = b->domain_off[r + 1] - d0;
+            const uint64_t h0 = alias ? 0 : (b->host_off ? b->host_off[r] : r * b->host_stride);
+            const uint32_t H = alias ? 0 : (b->host_off ? b->host_off[r + 1] - b->host_off[r] : b->host_stride);
+            out_off[r] = base + local[tt];
+            if (generic) {
+                GuardedWords ds{(const uint32_t *)b->domain_bytes}, hs{(const uint32_t *)b->host_bytes};
+                ByteSink sink;
+                sink.init(out_bytes + base + local[tt]);
+                if (alias)
+                    emit_path<true>(ds, d0, L, hs, (uint32_t)h0, H, sink);
+                else
+                    emit_path<false>(ds, d0, L, hs, (uint32_t)h0, H, sink);
+                if ((uint64_t)(sink.p - (out_bytes + base + local[tt])) != len[tt])
+                    abort();
+            } else {
+                PaddedWords ds{sdom.data()}, hs{shost.data()};
+                WordSink sink;
+                sink.init(sout.data(), local[tt] + shift);
+                if (alias)
+                    emit_path<true>(ds, (uint32_t)(d0 - da0), L, hs, (uint32_t)(h0 - ha0), H, sink);
+                else
+                    emit_path<false>(ds, (uint32_t)(d0 - da0), L, hs, (uint32_t)(h0 - ha0), H, sink);
+                sink.finish();
+            }
+        }
+        if (!generic)
+            memcpy(out_bytes + base, (const uint8_t *)sout.data() + shift, total);
+        base += total;
+    }
+    out_off[n] = base;
+    if (first_bad)
+        *first_bad = fb;
+    return bad_all;
+}
+
+/* frag blob: same layout regk_set_types builds (TypeFrag[] then word-aligned fragments) */
+uint32_t emul_jsons(const regk_batch *b, const uint8_t *blob, uint32_t ntypes, int generic, uint8_t *out_bytes,
+    uint64_t *out_off, uint64_t *first_bad)
+{
+    const uint64_t n = b->n;
+    uint32_t bad_all = 0;
+    uint64_t fb = UINT64_MAX;
+    uint64_t base = 0;
+    const PaddedWords fsrc{(const uint32_t *)blob};
+    const GuardedWords asrc{(const uint32_t *)b->addr_bytes};
+    for (uint64_t r0 = 0; r0 < n; r0 += TILE) {
+        const uint32_t nrec = (uint32_t)std::min<uint64_t>(TILE, n - r0);
+        struct Rec {
+            TypeFrag tf;
+            uint32_t aw[4];
+            uint32_t a0, al, k, p0;
+            int32_t ttl;
+            bool has_ttl, has_ports;
+            uint32_t len, local;
+        };
+        std::vector<Rec> rec(nrec);
+        uint32_t total = 0;
+        for (uint32_t t = 0; t < nrec; t++) {
+            const uint64_t r = r0 + t;
+            Rec &q = rec[t];
+            uint32_t bad = 0;
+            uint32_t tid = b->type_id[r];
+            if (tid >= ntypes) {
+                bad |= BAD_TYPE_ID;
+                tid = 0;
+            }
+            q.tf = ((const TypeFrag *)blob)[tid];
+            q.a0 = b->addr_off[r];
+            q.al = b->addr_off[r + 1] - q.a0;
+            q.ttl = b->ttl ? b->ttl[r] : INT32_MIN;
+            q.has_ttl = q.ttl != INT32_MIN;
+            q.p0 = 0;
+            q.k = 0;
+            if (b->ports_off) {
+                q.p0 = b->ports_off[r];
+                q.k = b->ports_off[r + 1] - q.p0;
+            }
+            q.has_ports = b->ports_present ? b->ports_present[r] != 0 : q.k > 0;
+            if (!q.has_ports)
+                q.k = 0;
+            memset(q.aw, 0, sizeof q.aw);
+            {
+                const uint32_t n16 = q.al < 16u ? q.al : 16u;
+                const uint32_t sh = (q.a0 & 3u) * 8u;
+                uint32_t wi = q.a0 >> 2;
+                uint32_t lo = n16 ? asrc.word(wi) : 0u;
+                for (uint32_t w = 0; w < 4; w++) {
+                    if (n16 > 4u * w) {
+                        const uint32_t nb = std::min(4u, n16 - 4u * w);
+                        const uint32_t hi = asrc.word_hi(wi + 1, sh + 8u * nb > 32u || n16 > 4u * (w + 1));
+                        const uint32_t keep = low_bytes(nb);
+                        q.aw[w] = funnel_r(lo, hi, sh) & keep;
+                        if (addr_word_bad(q.aw[w], keep))
+                            bad |= BAD_ADDR_BYTE;
+                        lo = hi;
+                        wi++;
+                    }
+                }
+                for (uint32_t i = q.a0 + 16u; i < q.a0 + q.al; i++) {
+                    const uint32_t c = b->addr_bytes[i];
+                    if (c < 0x20u || c >= 0x80u || c == 0x22u || c == 0x5Cu)
+                        bad |= BAD_ADDR_BYTE;
+                }
+            }
+            uint32_t pd = 0;
+            for (uint32_t i = 0; i < q.k; i++)
+                pd += ndigits_u32(b->ports[q.p0 + i]);
+            q.len = json_length(q.tf.f1_len, q.tf.f2_len, q.al, q.has_ttl, q.ttl, q.has_ports, q.k, pd);
+            q.local = total;
+            total += q.len;
+            if (bad) {
+                bad_all |= bad;
+                fb = std::min<uint64_t>(fb, r);
+            }
+        }
+        const uint32_t shift = (uint32_t)(base & 15);
+        std::vector<uint32_t> sout((shift + total) / 4 + 16, 0xEEEEEEEEu);
+        for (uint32_t tt = nrec; tt-- > 0;) {
+            const uint64_t r = r0 + tt;
+            Rec &q = rec[tt];
+            out_off[r] = base + q.local;
+            const uint32_t *ports = b->ports + q.p0;
+            auto port = [ports](uint32_t i) { return ports[i]; };
+            if (generic) {
+                ByteSink sink;
+                sink.init(out_bytes + base + q.local);
+                emit_json(fsrc, q.tf, q.aw, asrc, q.a0, q.al, q.has_ttl, q.ttl, q.has_ports, q.k, port, sink);
+                if ((uint64_t)(sink.p - (out_bytes + base + q.local)) != q.len)
+                    abort();
+            } else {
+                WordSink sink;
+                sink.init(sout.data(), q.local + shift);
+                emit_json(fsrc, q.tf, q.aw, asrc, q.a0, q.al, q.has_ttl, q.ttl, q.has_ports, q.k, port, sink);
+                sink.finish();
+            }
+        }
+        if (!generic)
+            memcpy(out_bytes + base, (const uint8_t *)sout.data() + shift, total);
+        base += total;
+    }
+    out_off[n] = base;
+    if (first_bad)
+        *first_bad = fb;
+    return bad_all;
+}
+
+uint32_t emul_dec(uint32_t v, uint8_t *out)
+{
+    ByteSink s;
+    s.init(out);
+    put_u32_dec(v, s);
+    return (uint32_t)(s.p - out);
+}
+
+uint32_t emul_ndigits(uint32_t v)
+{
+    return ndigits_u32(v);
+}
+
+}  /* extern "C" */
+
+#include "../../registrar_b200/csrc/regk_types.hpp"
+
+extern "C" int emul_build_blob(const char *const *types, const uint32_t *lens, uint32_t ntypes, uint8_t *blob_out,
+    uint32_t blob_cap, uint32_t *blob_len, uint32_t *max_escaped)
+{
+    std::vector<std::string> raw(ntypes);
+    for (uint32_t i = 0; i < ntypes; i++)
+        raw[i].assign(types[i], lens[i]);
+    std::vector<uint8_t> blob;
+    std::string why;
+    int rc = regk::build_type_blob(raw, &blob, max_escaped, &why);
+    if (rc)
+        return rc;
+    if (blob.size() > blob_cap)
+        return 3;
+    memcpy(blob_out, blob.data(), blob.size());
+    *blob_len = (uint32_t)blob.size();
+    return 0;
+}

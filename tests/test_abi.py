@@ -1,0 +1,62 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/regk.h declares
+(no compute calls here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "regk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(regk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(built):
+    import __graft_entry__ as g
+    from registrar_b200 import _native
+    g.build_cuda()
+    lib = _native.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), "libregk.so does not export %s" % s
+    assert sorted(_native.EXPORTS) == syms
+    assert lib.regk_abi_version() == 1
+
+
+def test_no_gpu_means_failure_not_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from registrar_b200 import _native
+    with pytest.raises(_native.RegkError) as ei:
+        _native.Context(0)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_struct_layouts_match_header(built):
+    # sizeof/offsetof as the C compiler sees them vs the ctypes mirrors
+    import ctypes as C
+    import subprocess
+    import tempfile
+    from registrar_b200 import _native
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "regk.h"
+    int main(void) {
+        printf("%zu %zu %zu %zu %zu %zu\n", sizeof(regk_batch), offsetof(regk_batch, domain_bytes),
+               offsetof(regk_batch, ports_present), sizeof(regk_result), offsetof(regk_result, json_total),
+               offsetof(regk_result, opaque));
+        return 0;
+    }'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
+    got = [C.sizeof(_native.CBatch), _native.CBatch.domain_bytes.offset, _native.CBatch.ports_present.offset,
+           C.sizeof(_native.CResult), _native.CResult.json_total.offset, _native.CResult.opaque.offset]
+    assert [int(x) for x in out] == got

@@ -1,0 +1,181 @@
+"""Parity of the sm_100a kernels with the oracle, through the C-ABI (libregk.so).
+
+Bit-exact: paths, payloads and both offset arrays (integer/byte work, no tolerance).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from registrar_b200 import synth
+from registrar_b200.batch import (BAD_ADDR_BYTE, BAD_DOMAIN_BYTE, BAD_HOST_BYTE, BAD_TYPE_ID, RecordBatch)
+from test_core_emul import EDGE_DOMAINS, _edge_records
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    from registrar_b200 import _native
+    c = _native.Context(0)
+    yield c
+    c.close()
+
+
+def assert_same(got, want):
+    assert want.bad_bits == 0
+    assert np.array_equal(got.path_off, want.path_off), "path offsets"
+    assert np.array_equal(got.json_off, want.json_off), "payload offsets"
+    if not np.array_equal(got.path_bytes, want.path_bytes):
+        i = int(np.argmax(got.path_bytes != want.path_bytes))
+        r = int(np.searchsorted(want.path_off, i, side="right") - 1)
+        raise AssertionError("path %d: %r != %r" % (r, got.path(r), want.path(r)))
+    if not np.array_equal(got.json_bytes, want.json_bytes):
+        i = int(np.argmax(got.json_bytes != want.json_bytes))
+        r = int(np.searchsorted(want.json_off, i, side="right") - 1)
+        raise AssertionError("payload %d: %r != %r" % (r, got.json(r), want.json(r)))
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("config,n", [("config1", 1000), ("config2", 100_000), ("config3", 100_000),
+                                      ("config5", 100_000), ("config3", 257), ("config3", 1), ("config5", 256)])
+def test_synthetic(ctx, config, n, generic):
+    ctx.set_option("force_generic", generic)
+    try:
+        batch = synth.generate(config, n=n)
+        assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
+    finally:
+        ctx.set_option("force_generic", 0)
+
+
+def test_config2_full_size(ctx):
+    batch = synth.generate("config2")
+    got = ctx.register_batch(batch)
+    assert_same(got, oracle.register_batch(batch))
+    assert got.launches == 2
+
+
+@pytest.mark.parametrize("start", [1, 7, 255, 1001, 99_999_999_000])
+def test_shards_anywhere_in_the_stream(ctx, start):
+    batch = synth.generate("config3", n=3000, start=start)
+    assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+@pytest.mark.parametrize("alias", [False, True])
+def test_edge_cases(ctx, alias, generic):
+    ctx.set_option("force_generic", generic)
+    try:
+        batch = RecordBatch.from_records(_edge_records(), alias=alias)
+        assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
+    finally:
+        ctx.set_option("force_generic", 0)
+
+
+def test_tiny_smem_budget_takes_generic_path(ctx):
+    # capacity smaller than one tile's bytes: every tile must fall back to the generic (global) path
+    ctx.set_option("dom_cap", 256)
+    ctx.set_option("json_out_cap", 256)
+    try:
+        batch = synth.generate("config5", n=5000)
+        assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
+    finally:
+        ctx.set_option("dom_cap", 0)
+        ctx.set_option("json_out_cap", 0)
+
+
+def test_long_records_mixed_paths(ctx):
+    # a few very long domains among short ones: some tiles fit shared memory, some do not
+    recs = []
+    for i in range(2000):
+        d = b".".join([b"l" * 63] * 6) if i % 517 == 0 else b"svc%d.example.com" % i
+        recs.append({"domain": d, "hostname": b"a2674d3b-a9c4-46bc-a835-b6ce21d522c2", "type": b"host",
+                     "address": b"10.1.2.%d" % (i % 250), "ttl": 30 if i % 2 else None,
+                     "ports": [80, 443] if i % 3 == 0 else None})
+    ctx.set_option("dom_cap", 6000)
+    try:
+        batch = RecordBatch.from_records(recs)
+        assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
+    finally:
+        ctx.set_option("dom_cap", 0)
+
+
+def test_variable_hostnames(ctx):
+    recs = [{"domain": b"a%d.b.c" % i, "hostname": b"h" * (1 + i % 40), "type": b"host", "address": b"1.1.1.1"}
+            for i in range(1500)]
+    batch = RecordBatch.from_records(recs)
+    assert batch.host_off is not None
+    assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
+
+
+def test_paths_only_and_payloads_only(ctx):
+    batch = synth.generate("config3", n=5000)
+    want = oracle.register_batch(batch)
+    got = ctx.register_batch(batch, payloads=False)
+    assert np.array_equal(got.path_bytes, want.path_bytes) and got.launches == 1
+    got = ctx.register_batch(batch, paths=False)
+    assert np.array_equal(got.json_bytes, want.json_bytes) and got.launches == 1
+
+
+def test_known_answers(ctx):
+    # lib/register.js:37, README.md:50-54, test/register.test.js:122-130,145-153, README.md:539-547,623-630
+    recs = [
+        {"domain": "1.moray.us-east.joyent.com", "hostname": "h", "type": "host", "address": "127.0.0.1"},
+        {"domain": "authcache.emy-10.joyent.us", "hostname": "a2674d3b-a9c4-46bc-a835-b6ce21d522c2",
+         "type": "redis_host", "address": "172.27.10.62", "ttl": 30, "ports": [6379]},
+        {"domain": "test.laptop.joyent.us", "hostname": "myhost", "type": "host", "address": "127.0.0.1", "ttl": 120},
+        {"domain": "x.emy-10.joyent.us", "hostname": "lb0", "type": "load_balancer", "address": "172.27.10.72",
+         "ports": [80]},
+    ]
+    got = ctx.register_batch(RecordBatch.from_records(recs))
+    assert got.path(0) == b"/com/joyent/us-east/moray/1/h"
+    assert got.json(0) == b'{"type":"host","address":"127.0.0.1","host":{"address":"127.0.0.1"}}'
+    assert got.path(1) == b"/us/joyent/emy-10/authcache/a2674d3b-a9c4-46bc-a835-b6ce21d522c2"
+    assert got.json(1) == (b'{"type":"redis_host","address":"172.27.10.62","ttl":30,'
+                           b'"redis_host":{"address":"172.27.10.62","ports":[6379]}}')
+    assert got.json(2) == b'{"type":"host","address":"127.0.0.1","ttl":120,"host":{"address":"127.0.0.1"}}'
+    assert got.json(3) == (b'{"type":"load_balancer","address":"172.27.10.72",'
+                           b'"load_balancer":{"address":"172.27.10.72","ports":[80]}}')
+    alias = ctx.register_batch(RecordBatch.from_records(recs, alias=True))
+    assert alias.path(0) == b"/com/joyent/us-east/moray/1"
+
+
+def test_out_of_domain_is_an_error_not_a_fallback(ctx):
+    from registrar_b200._native import OutOfDomainError
+    base = {"domain": b"a.b", "hostname": b"h", "type": b"host", "address": b"1.2.3.4"}
+    for patch, bit in [({"domain": b"a/b.c"}, BAD_DOMAIN_BYTE), ({"domain": b"caf\xc3\xa9.org"}, BAD_DOMAIN_BYTE),
+                       ({"hostname": b".."}, BAD_HOST_BYTE), ({"hostname": b"a/b"}, BAD_HOST_BYTE),
+                       ({"address": b'1.2"3'}, BAD_ADDR_BYTE), ({"address": b"1\n2"}, BAD_ADDR_BYTE)]:
+        recs = [dict(base) for _ in range(700)]
+        recs[300].update(patch)
+        recs[650].update(patch)
+        with pytest.raises(OutOfDomainError) as ei:
+            ctx.register_batch(RecordBatch.from_records(recs))
+        assert ei.value.result.bad_bits == bit
+        assert ei.value.result.first_bad == 300
+    batch = RecordBatch.from_records([dict(base) for _ in range(10)])
+    batch.type_id[4] = 9
+    with pytest.raises(OutOfDomainError) as ei:
+        ctx.register_batch(batch)
+    assert ei.value.result.bad_bits == BAD_TYPE_ID and ei.value.result.first_bad == 4
+    # and the context still works afterwards
+    got = ctx.register_batch(RecordBatch.from_records([dict(base)]))
+    assert got.path(0) == b"/b/a/h"
+
+
+def test_rejected_type_names(ctx):
+    from registrar_b200._native import OutOfDomainError
+    for t in ("type", "address", "ttl", "0", "42"):
+        with pytest.raises(OutOfDomainError):
+            ctx.set_types([t])
+    ctx.set_types(["00", "quote\"d", "host"])     # "00" is not an array index; escapes are applied on the host
+    rec = {"domain": "a.b", "hostname": "h", "type": 'quote"d', "address": "1.2.3.4"}
+    batch = RecordBatch.from_records([rec], types=["00", 'quote"d', "host"])
+    got = ctx.register_batch(batch)
+    assert got.json(0) == oracle.register_batch(batch).json(0)
+    assert got.json(0).startswith(b'{"type":"quote\\"d"')
+
+
+def test_empty_batch(ctx):
+    batch = RecordBatch.from_records([], types=["host"])
+    got = ctx.register_batch(batch)
+    assert got.n == 0 and got.path_total == 0 and got.json_total == 0

@@ -1,0 +1,31 @@
+"""Quick device timing of the two kernels on the named configs (development aid; bench.py is the contract)."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from registrar_b200 import _native, synth
+from registrar_b200.batch import RecordBatch
+
+def main():
+    ctx = _native.Context(0)
+    out = []
+    for cfg, n in [("config2", 1_000_000), ("config3", 2_000_000), ("config5", 2_000_000)]:
+        b = synth.generate(cfg, n=n)
+        for generic in (0, 1):
+            ctx.set_option("force_generic", generic)
+            ms = []
+            for it in range(6):
+                r = ctx.register_batch(b, copy=False)
+                ms.append((r.path_kernel_ms, r.json_kernel_ms))
+            ms = ms[2:]
+            p = min(m[0] for m in ms); j = min(m[1] for m in ms)
+            alg = b.input_bytes() + RecordBatch.output_bytes(r.path_total, r.json_total, b.n)
+            rec = dict(config=cfg, n=n, generic=generic, path_ms=p, json_ms=j, alg_bytes=alg,
+                       gbps=alg / ((p + j) * 1e-3) / 1e9, grec_s=n / ((p + j) * 1e-3) / 1e9)
+            print(json.dumps(rec), flush=True)
+            out.append(rec)
+    ctx.set_option("force_generic", 0)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/quick_time.json", "w"), indent=1)
+
+if __name__ == "__main__":
+    main()
