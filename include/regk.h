@@ -57,7 +57,8 @@ extern "C" {
 #define REGK_BAD_DOMAIN_BYTE  (1u << 0)  /* byte >= 0x80 or '/' in a domain (JS toLowerCase / path.normalize
                                             semantics are only restated for ASCII, slash-free labels) */
 #define REGK_BAD_HOST_BYTE    (1u << 1)  /* hostname empty, ".", "..", or has byte >= 0x80, NUL or '/' */
-#define REGK_BAD_ADDR_BYTE    (1u << 2)  /* address byte outside 0x20..0x7f or needing a JSON escape (" or \) */
+#define REGK_BAD_ADDR_BYTE    (1u << 2)  /* address empty (a falsy adminIp means auto-detect, register.js:143), or a byte
+                                            outside 0x20..0x7f or needing a JSON escape (" or \) */
 #define REGK_BAD_TYPE_ID      (1u << 3)  /* type_id >= number of types set */
 #define REGK_BAD_TOO_LARGE    (1u << 4)  /* a single record's path or payload exceeds 2^31 bytes */
 

@@ -51,18 +51,20 @@ def node_join(*parts: str) -> str:
 
 
 def node_dirname(p: str) -> str:
-    if p == "":
+    # node >= 6 posix path.dirname (production registrar runs node v6.17.0, Makefile:28): the directory part
+    # keeps whatever precedes the last separator run's final slash, e.g. '/b//a' -> '/b/'
+    if not p:
         return "."
-    stripped = p.rstrip("/")
-    if stripped == "":
-        return "/"
-    i = stripped.rfind("/")
-    if i < 0:
-        return "."
-    head = stripped[:i].rstrip("/")
-    if head == "":
-        return "//" if p.startswith("/") and i == 1 else "/"
-    return head
+    has_root = p[0] == "/"
+    i = len(p) - 1
+    while i >= 1 and p[i] == "/":
+        i -= 1
+    j = p.rfind("/", 1, i + 1)
+    if j == -1:
+        return "/" if has_root else "."
+    if has_root and j == 1:
+        return "//"
+    return p[:j]
 
 
 def host_node_path(domain: str, hostname: str) -> str:

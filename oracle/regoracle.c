@@ -327,6 +327,8 @@ RO_EXPORT uint32_t ro_validate_record(const uint8_t *d, size_t L, const uint8_t 
         }
     }
     if (!no_json) {
+        if (al == 0)                    /* falsy adminIp means "auto-detect" in the reference (register.js:143) */
+            bad |= REGK_BAD_ADDR_BYTE;
         for (size_t i = 0; i < al; i++)
             if (a[i] < 0x20 || a[i] >= 0x80 || a[i] == '"' || a[i] == '\\')
                 bad |= REGK_BAD_ADDR_BYTE;

@@ -43,7 +43,6 @@ struct regk_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;              /* the stream work is enqueued on */
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     std::string err;
     int sm_count = 0;
     int max_smem_optin = 0;
@@ -59,16 +58,25 @@ struct regk_ctx {
     /* outputs */
     DevBuf path_bytes, path_off, json_bytes, json_off;
     HostBuf h_path_bytes, h_path_off, h_json_bytes, h_json_off;
-    /* workspace: DevStatus | tickets | tile status */
+    /* workspace: DevStatus | tickets | tile status (stream-ordered reuse) */
     DevBuf work;
-    DevStatus *h_status = nullptr;              /* pinned */
 
-    /* pending batch (single slot) */
-    bool pending = false;
-    bool timing_valid = false;
-    uint64_t pend_n = 0;
-    uint32_t pend_flags = 0;
-    uint32_t pend_launches = 0;
+    /* in-flight batches: events + pinned status per slot.  Outputs are single-buffered: with the
+       "async" option several batches may be enqueued back to back (benchmark loops), each one
+       overwriting the previous batch's outputs in stream order. */
+    struct Slot {
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+        DevStatus *h_status = nullptr;          /* pinned */
+        bool in_use = false;
+        uint64_t n = 0;
+        uint32_t flags = 0;
+        uint32_t launches = 0;
+    };
+    static constexpr int NSLOTS = 64;
+    Slot slots[NSLOTS];
+    DevStatus *h_status_block = nullptr;        /* pinned, NSLOTS entries */
+    uint64_t seq = 0;
+    int pending = 0;
 
     std::map<std::string, int64_t> opt;
 };
@@ -197,10 +205,13 @@ int regk_create(int device, regk_ctx **out)
     ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     CKC(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
-    for (auto &ev : ctx->ev)
-        CKC(cudaEventCreate(&ev));
-    CKC(cudaMallocHost((void **)&ctx->h_status, sizeof(DevStatus)));
-    memset(ctx->h_status, 0, sizeof(DevStatus));
+    CKC(cudaMallocHost((void **)&ctx->h_status_block, sizeof(DevStatus) * regk_ctx::NSLOTS));
+    memset(ctx->h_status_block, 0, sizeof(DevStatus) * regk_ctx::NSLOTS);
+    for (int i = 0; i < regk_ctx::NSLOTS; i++) {
+        for (auto &ev : ctx->slots[i].ev)
+            CKC(cudaEventCreate(&ev));
+        ctx->slots[i].h_status = ctx->h_status_block + i;
+    }
 #undef CKC
     *out = ctx;
     return REGK_OK;
@@ -221,11 +232,12 @@ void regk_destroy(regk_ctx *ctx)
     for (HostBuf *b : {&ctx->h_path_bytes, &ctx->h_path_off, &ctx->h_json_bytes, &ctx->h_json_off})
         if (b->p)
             cudaFreeHost(b->p);
-    if (ctx->h_status)
-        cudaFreeHost(ctx->h_status);
-    for (auto &ev : ctx->ev)
-        if (ev)
-            cudaEventDestroy(ev);
+    if (ctx->h_status_block)
+        cudaFreeHost(ctx->h_status_block);
+    for (auto &sl : ctx->slots)
+        for (auto &ev : sl.ev)
+            if (ev)
+                cudaEventDestroy(ev);
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -365,8 +377,12 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
 {
     if (!ctx || !b || !res)
         return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: NULL argument");
-    if (ctx->pending)
+    const bool async = opt_get(ctx, "async", 0) != 0;
+    if (ctx->pending && !async)
         return fail(ctx, REGK_ERR_STATE, "regk_register_batch: previous batch not finished (regk_finish)");
+    regk_ctx::Slot &slot = ctx->slots[ctx->seq % regk_ctx::NSLOTS];
+    if (slot.in_use)
+        return fail(ctx, REGK_ERR_STATE, "regk_register_batch: %d batches in flight; call regk_finish", regk_ctx::NSLOTS);
     memset(res, 0, sizeof *res);
     const uint64_t n = b->n;
     const bool in_dev = b->flags & REGK_IN_DEVICE;
@@ -470,7 +486,7 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     }
     uint32_t launches = 0;
     const uint32_t force_generic = (uint32_t)opt_get(ctx, "force_generic", 0);
-    CK(cudaEventRecord(ctx->ev[0], s));
+    CK(cudaEventRecord(slot.ev[0], s));
     if (n && do_path) {
         PathParams p{};
         p.n = n;
@@ -516,7 +532,7 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         CK(cudaGetLastError());
         launches++;
     }
-    CK(cudaEventRecord(ctx->ev[1], s));
+    CK(cudaEventRecord(slot.ev[1], s));
     if (n && do_json) {
         JsonParams p{};
         p.n = n;
@@ -555,18 +571,21 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         CK(cudaGetLastError());
         launches++;
     }
-    CK(cudaEventRecord(ctx->ev[2], s));
-    CK(cudaMemcpyAsync(ctx->h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(slot.ev[2], s));
+    CK(cudaMemcpyAsync(slot.h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(slot.ev[3], s));
 
-    ctx->pending = true;
-    ctx->pend_n = n;
-    ctx->pend_flags = b->flags;
-    ctx->pend_launches = launches;
+    slot.in_use = true;
+    slot.n = n;
+    slot.flags = b->flags;
+    slot.launches = launches;
+    ctx->seq++;
+    ctx->pending++;
     res->n = n;
     res->flags = out_dev ? REGK_OUT_DEVICE : 0;
     res->launches = launches;
-    res->opaque = ctx;
-    if (opt_get(ctx, "async", 0))
+    res->opaque = &slot;
+    if (async)
         return REGK_OK;
     return regk_finish(ctx, res);
 }
@@ -575,25 +594,27 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
 {
     if (!ctx || !res)
         return fail(ctx, REGK_ERR_INVALID_ARG, "regk_finish: NULL argument");
-    if (!ctx->pending)
-        return fail(ctx, REGK_ERR_STATE, "regk_finish: nothing pending");
+    regk_ctx::Slot *slot = (regk_ctx::Slot *)res->opaque;
+    if (!slot || slot < ctx->slots || slot >= ctx->slots + regk_ctx::NSLOTS || !slot->in_use)
+        return fail(ctx, REGK_ERR_STATE, "regk_finish: this result has no batch in flight");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    cudaError_t e = cudaStreamSynchronize(s);
-    ctx->pending = false;
+    cudaError_t e = cudaEventSynchronize(slot->ev[3]);
+    slot->in_use = false;
+    ctx->pending--;
     if (e != cudaSuccess)
         return fail(ctx, REGK_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
-    const DevStatus st = *ctx->h_status;
-    const uint64_t n = ctx->pend_n;
-    const bool out_dev = ctx->pend_flags & REGK_OUT_DEVICE;
+    const DevStatus st = *slot->h_status;
+    const uint64_t n = slot->n;
+    const bool out_dev = slot->flags & REGK_OUT_DEVICE;
     float ms_p = 0, ms_j = 0;
-    cudaEventElapsedTime(&ms_p, ctx->ev[0], ctx->ev[1]);
-    cudaEventElapsedTime(&ms_j, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ms_p, slot->ev[0], slot->ev[1]);
+    cudaEventElapsedTime(&ms_j, slot->ev[1], slot->ev[2]);
     res->n = n;
     res->path_kernel_ms = ms_p;
     res->json_kernel_ms = ms_j;
     res->kernel_ms = ms_p + ms_j;
-    res->launches = ctx->pend_launches;
+    res->launches = slot->launches;
     res->bad_bits = st.bad_bits;
     res->first_bad = st.bad_bits ? ~st.first_bad : 0;
     res->path_total = st.path_total;
@@ -615,7 +636,7 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
         return REGK_OK;
     }
     int rc;
-    const bool do_path = !(ctx->pend_flags & REGK_NO_PATH), do_json = !(ctx->pend_flags & REGK_NO_JSON);
+    const bool do_path = !(slot->flags & REGK_NO_PATH), do_json = !(slot->flags & REGK_NO_JSON);
     if ((rc = ensure_host(ctx, ctx->h_path_bytes, st.path_total + 16)) || (rc = ensure_host(ctx, ctx->h_path_off, (n + 1) * 8)) ||
         (rc = ensure_host(ctx, ctx->h_json_bytes, st.json_total + 16)) || (rc = ensure_host(ctx, ctx->h_json_off, (n + 1) * 8)))
         return rc;

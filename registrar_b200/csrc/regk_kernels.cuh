@@ -409,6 +409,8 @@ __global__ void __launch_bounds__(TILE, 3) regk_json_kernel(const JsonParams p)
         a1 = a0;
     }
     const uint32_t al = a1 - a0;
+    if (al == 0)
+        bad |= BAD_ADDR_BYTE;           /* a falsy adminIp means "auto-detect" upstream (register.js:143) */
     const int32_t ttl = p.ttl ? p.ttl[r] : INT32_MIN;
     const bool has_ttl = ttl != INT32_MIN;
     uint32_t p0 = 0, k = 0;

@@ -150,6 +150,8 @@ uint32_t emul_jsons(const regk_batch *b, const uint8_t *blob, uint32_t ntypes, i
             q.tf = ((const TypeFrag *)blob)[tid];
             q.a0 = b->addr_off[r];
             q.al = b->addr_off[r + 1] - q.a0;
+            if (q.al == 0)
+                bad |= BAD_ADDR_BYTE;
             q.ttl = b->ttl ? b->ttl[r] : INT32_MIN;
             q.has_ttl = q.ttl != INT32_MIN;
             q.p0 = 0;

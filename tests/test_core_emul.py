@@ -87,7 +87,7 @@ def _edge_records(alias=False):
         for h in hosts:
             i += 1
             recs.append({"domain": d, "hostname": h, "type": [b"host", b"load_balancer", b"redis_host"][i % 3],
-                         "address": [b"127.0.0.1", b"1.2.3.4", b"255.255.255.255", b"", b"fe80::1ff:fe23:4567:890a%eth0",
+                         "address": [b"127.0.0.1", b"1.2.3.4", b"255.255.255.255", b"9", b"fe80::1ff:fe23:4567:890a%eth0",
                                      b"abcdefghijklmnop", b"abcdefghijklmnopq"][i % 7],
                          "ttl": [None, 0, 5, 30, 120, 3600, 86400, 2147483647, -1, -2147483647, 99999, 100000][i % 12],
                          "ports": [None, [], [80], [6379], [1, 22, 333, 4444, 55555], [65535, 0],
@@ -134,7 +134,7 @@ def test_fence(emul, generic):
         ({"hostname": b"h\xff"}, BAD_HOST_BYTE),
         ({"address": b'1.2"3'}, BAD_ADDR_BYTE), ({"address": b"1\\2"}, BAD_ADDR_BYTE),
         ({"address": b"1\n2"}, BAD_ADDR_BYTE), ({"address": b"\xe2\x82\xac"}, BAD_ADDR_BYTE),
-        ({"address": b"0123456789abcdefg\x01"}, BAD_ADDR_BYTE),
+        ({"address": b"0123456789abcdefg\x01"}, BAD_ADDR_BYTE), ({"address": b""}, BAD_ADDR_BYTE),
     ]
     for patch, bit in cases:
         for pos in (0, 3, 299):            # first tile, middle, second tile
@@ -160,7 +160,7 @@ def test_hypothesis_records(emul):
     label = st.text(alphabet="abcXYZ019-_", min_size=0, max_size=9)
     dom = st.lists(label, min_size=0, max_size=7).map(lambda ls: ".".join(ls).encode())
     host = st.text(alphabet="abcdef0123456789-.", min_size=1, max_size=40).filter(lambda s: s not in (".", "..")).map(str.encode)
-    addr = st.text(alphabet="0123456789.:abcdef", min_size=0, max_size=24).map(str.encode)
+    addr = st.text(alphabet="0123456789.:abcdef", min_size=1, max_size=24).map(str.encode)
     rec = st.fixed_dictionaries({
         "domain": dom, "hostname": host, "type": st.sampled_from([b"host", b"moray_host", b"t"]), "address": addr,
         "ttl": st.one_of(st.none(), st.integers(-2 ** 31 + 1, 2 ** 31 - 1)),

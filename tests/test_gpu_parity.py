@@ -179,3 +179,26 @@ def test_empty_batch(ctx):
     batch = RecordBatch.from_records([], types=["host"])
     got = ctx.register_batch(batch)
     assert got.n == 0 and got.path_total == 0 and got.json_total == 0
+
+
+@pytest.mark.parametrize("name", ["config1.jsonl", "edge.jsonl"])
+def test_golden_fixtures_from_the_executed_reference(ctx, name):
+    # BASELINE.json configs[0]: reference lib/register.js output on the 1k synthetic records, bit-exact
+    from golden_util import as_record, load
+    from registrar_b200._native import OutOfDomainError
+    rows = load(name)
+    recs = [as_record(r["in"]) for r in rows]
+    if name == "edge.jsonl":
+        # keep the rows inside the fence; the others must be refused (checked below)
+        one = [oracle.register_batch(RecordBatch.from_records([r])).bad_bits for r in recs]
+        outside = [r for r, b in zip(recs, one) if b]
+        assert 5 < len(outside) < len(recs) / 2
+        for r in outside[:8]:
+            with pytest.raises(OutOfDomainError):
+                ctx.register_batch(RecordBatch.from_records([r]))
+        rows = [row for row, b in zip(rows, one) if not b]
+        recs = [r for r, b in zip(recs, one) if not b]
+    got = ctx.register_batch(RecordBatch.from_records(recs))
+    for i, row in enumerate(rows):
+        assert got.path(i) == row["path"].encode("latin-1"), (i, row["in"])
+        assert got.json(i) == row["json"].encode("utf-8"), (i, row["in"])
