@@ -120,9 +120,10 @@ typedef struct regk_result {
     uint8_t        *json_bytes;
     uint64_t       *json_off;       /* [n+1] */
     uint64_t        json_total;     /* == json_off[n] */
-    float           kernel_ms;      /* device time of the path+payload kernels (CUDA events on the ctx stream) */
-    float           path_kernel_ms;
-    float           json_kernel_ms;
+    float           kernel_ms;      /* device time of all kernels of the batch (CUDA events on the ctx stream) */
+    float           path_kernel_ms; /* regk_path_kernel */
+    float           json_kernel_ms; /* regk_json_kernel */
+    float           json_len_kernel_ms; /* regk_json_len_kernel (payload lengths + tile bases) */
     uint32_t        launches;       /* kernels launched by this call */
     void           *opaque;         /* library bookkeeping */
 } regk_result;

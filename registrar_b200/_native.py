@@ -57,7 +57,7 @@ class CResult(C.Structure):          # regk_result
                 ("path_bytes", C.c_void_p), ("path_off", C.c_void_p), ("path_total", C.c_uint64),
                 ("json_bytes", C.c_void_p), ("json_off", C.c_void_p), ("json_total", C.c_uint64),
                 ("kernel_ms", C.c_float), ("path_kernel_ms", C.c_float), ("json_kernel_ms", C.c_float),
-                ("launches", C.c_uint32), ("opaque", C.c_void_p)]
+                ("json_len_kernel_ms", C.c_float), ("launches", C.c_uint32), ("opaque", C.c_void_p)]
 
 
 EXPORTS = ["regk_abi_version", "regk_create", "regk_destroy", "regk_last_error", "regk_set_stream",
@@ -135,11 +135,13 @@ class HostResult:
     """Host copy of a regk_result (NumPy views are copied out of the library's pinned buffers
     unless copy=False)."""
 
-    def __init__(self, n, path_bytes, path_off, json_bytes, json_off, kernel_ms, path_ms, json_ms, launches):
+    def __init__(self, n, path_bytes, path_off, json_bytes, json_off, kernel_ms, path_ms, json_ms, launches,
+                 json_len_ms=0.0):
         self.n = n
         self.path_bytes, self.path_off = path_bytes, path_off
         self.json_bytes, self.json_off = json_bytes, json_off
         self.kernel_ms, self.path_kernel_ms, self.json_kernel_ms = kernel_ms, path_ms, json_ms
+        self.json_len_kernel_ms = json_len_ms
         self.launches = launches
 
     @property
@@ -239,7 +241,8 @@ class Context:
         out = HostResult(
             n, cp(_as_np(res.path_bytes, int(res.path_total), np.uint8)), cp(_as_np(res.path_off, n + 1, np.uint64)),
             cp(_as_np(res.json_bytes, int(res.json_total), np.uint8)), cp(_as_np(res.json_off, n + 1, np.uint64)),
-            float(res.kernel_ms), float(res.path_kernel_ms), float(res.json_kernel_ms), int(res.launches))
+            float(res.kernel_ms), float(res.path_kernel_ms), float(res.json_kernel_ms), int(res.launches),
+            float(res.json_len_kernel_ms))
         self._lib.regk_release(self._h, C.byref(res))
         return out
 

@@ -65,7 +65,11 @@ struct regk_ctx {
        "async" option several batches may be enqueued back to back (benchmark loops), each one
        overwriting the previous batch's outputs in stream order. */
     struct Slot {
-        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+        cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        PathParams path_params{};               /* kept for the exact-offset redo (empty labels) */
+        size_t path_smem = 0;
+        bool path_alias = false, did_path = false;
+        DevStatus *d_status = nullptr;
         DevStatus *h_status = nullptr;          /* pinned */
         bool in_use = false;
         uint64_t n = 0;
@@ -426,8 +430,6 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: domain_bytes_len is required for device batches");
         if (do_json && addr_len == 0 && b->addr_bytes)
             return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: addr_bytes_len is required for device batches");
-        if (do_json && b->ports_off && ports_len == 0 && b->ports)
-            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: ports_len is required for device batches");
     }
     if (alias)
         host_len = 0;
@@ -467,18 +469,19 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         (rc = ensure_dev(ctx, ctx->json_bytes, json_cap)) || (rc = ensure_dev(ctx, ctx->json_off, (n + 1) * 8)))
         return rc;
 
-    /* ---- workspace ---- */
+    /* ---- workspace: status | counters | per-tile totals and bases of both kernels ---- */
     const uint64_t ntiles = (n + TILE - 1) / TILE;
-    const size_t status_off = 0, ticket_off = 64, tiles_off = 128;
-    const size_t work_bytes = tiles_off + 2 * ntiles * 8 + 64;
+    const size_t totals_p_off = 128;
+    const size_t bases_p_off = (totals_p_off + ntiles * 4 + 15) & ~(size_t)15;
+    const size_t totals_j_off = bases_p_off + (ntiles + 1) * 8;
+    const size_t bases_j_off = (totals_j_off + ntiles * 4 + 15) & ~(size_t)15;
+    const size_t work_bytes = bases_j_off + (ntiles + 1) * 8 + 64;
     if ((rc = ensure_dev(ctx, ctx->work, work_bytes)))
         return rc;
     uint8_t *wk = (uint8_t *)ctx->work.p;
-    CK(cudaMemsetAsync(wk, 0, work_bytes, s));
-    DevStatus *d_status = (DevStatus *)(wk + status_off);
-    uint32_t *tickets = (uint32_t *)(wk + ticket_off);
-    unsigned long long *tiles_p = (unsigned long long *)(wk + tiles_off);
-    unsigned long long *tiles_j = tiles_p + ntiles;
+    CK(cudaMemsetAsync(wk, 0, 128, s));
+    DevStatus *d_status = (DevStatus *)wk;
+    uint32_t *counters = (uint32_t *)(wk + 64);
 
     if (n == 0) {
         CK(cudaMemsetAsync(ctx->path_off.p, 0, 8, s));
@@ -486,6 +489,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     }
     uint32_t launches = 0;
     const uint32_t force_generic = (uint32_t)opt_get(ctx, "force_generic", 0);
+    slot.did_path = false;
+    slot.d_status = d_status;
     CK(cudaEventRecord(slot.ev[0], s));
     if (n && do_path) {
         PathParams p{};
@@ -498,17 +503,20 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         p.out_bytes = (uint8_t *)ctx->path_bytes.p;
         p.out_off = (unsigned long long *)ctx->path_off.p;
         p.out_capacity = path_cap;
-        p.scan.tile_status = tiles_p;
-        p.scan.ticket = tickets + 0;
-        p.scan.base_in = nullptr;
+        p.tile_base = nullptr;                  /* closed-form offsets; see regk_finish for the exact redo */
+        p.tile_total = (uint32_t *)(wk + totals_p_off);
+        p.tile_base_out = (unsigned long long *)(wk + bases_p_off);
+        p.counter = counters + 0;
         p.status = d_status;
+        p.dom_limit = dom_len;
+        p.host_limit = host_len;
         p.force_generic = force_generic;
-        /* shared-memory budget: twice the mean tile, clamped; tiles that do not fit go generic */
+        /* shared-memory budget: 1.5x the mean tile, clamped; tiles that do not fit go generic */
         const uint64_t mean_dom_tile = dom_len / std::max<uint64_t>(ntiles, 1) + 1;
         uint32_t dom_cap = (uint32_t)opt_get(ctx, "dom_cap", 0);
         if (!dom_cap)
             dom_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(align16(mean_dom_tile * 3 / 2 + 512), 4096), 49152);
-        dom_cap = (uint32_t)align16(dom_cap);
+        dom_cap = (uint32_t)((dom_cap + 127) & ~127u);         /* bitmap region stays 16-byte aligned */
         uint32_t host_cap = 0;
         if (!alias) {
             const uint64_t mean_host_tile = p.host_off ? host_len / std::max<uint64_t>(ntiles, 1) + 1
@@ -516,7 +524,7 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             host_cap = (uint32_t)std::min<uint64_t>(align16((p.host_off ? mean_host_tile * 3 / 2 + 512 : mean_host_tile) + 16), 49152);
         }
         uint32_t out_cap = (uint32_t)align16((uint64_t)dom_cap + host_cap + 2 * TILE + 32);
-        size_t smem = (size_t)dom_cap + 32 + (alias ? 0 : host_cap + 32) + out_cap + 32;
+        size_t smem = (size_t)dom_cap + 32 + dom_cap / 8 + 16 + (alias ? 0 : host_cap + 32) + out_cap + 32;
         if (smem > (size_t)ctx->max_smem_optin)
             return fail(ctx, REGK_ERR_INVALID_ARG, "path kernel needs %zu B of shared memory (> %d)", smem, ctx->max_smem_optin);
         p.dom_cap = dom_cap;
@@ -531,6 +539,10 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         }
         CK(cudaGetLastError());
         launches++;
+        slot.path_params = p;
+        slot.path_smem = smem;
+        slot.path_alias = alias;
+        slot.did_path = true;
     }
     CK(cudaEventRecord(slot.ev[1], s));
     if (n && do_json) {
@@ -549,10 +561,12 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         p.out_bytes = (uint8_t *)ctx->json_bytes.p;
         p.out_off = (unsigned long long *)ctx->json_off.p;
         p.out_capacity = json_cap;
-        p.scan.tile_status = tiles_j;
-        p.scan.ticket = tickets + 1;
-        p.scan.base_in = nullptr;
+        p.tile_total = (uint32_t *)(wk + totals_j_off);
+        p.tile_base = (unsigned long long *)(wk + bases_j_off);
+        p.counter = counters + 1;
         p.status = d_status;
+        p.addr_limit = addr_len;
+        p.ports_limit = ports_len;
         p.force_generic = force_generic;
         uint32_t out_cap = (uint32_t)opt_get(ctx, "json_out_cap", 0);
         if (!out_cap) {
@@ -566,14 +580,20 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         size_t smem = (size_t)p.blob_bytes + out_cap + 32;
         if (smem > (size_t)ctx->max_smem_optin)
             return fail(ctx, REGK_ERR_INVALID_ARG, "json kernel needs %zu B of shared memory (> %d)", smem, ctx->max_smem_optin);
+        regk_json_len_kernel<<<(unsigned)ntiles, TILE, 0, s>>>(p);
+        CK(cudaGetLastError());
+        launches++;
+        CK(cudaEventRecord(slot.ev[2], s));
         CK(cudaFuncSetAttribute(regk_json_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         regk_json_kernel<<<(unsigned)ntiles, TILE, smem, s>>>(p);
         CK(cudaGetLastError());
         launches++;
+    } else {
+        CK(cudaEventRecord(slot.ev[2], s));
     }
-    CK(cudaEventRecord(slot.ev[2], s));
-    CK(cudaMemcpyAsync(slot.h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
     CK(cudaEventRecord(slot.ev[3], s));
+    CK(cudaMemcpyAsync(slot.h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(slot.ev[4], s));
 
     slot.in_use = true;
     slot.n = n;
@@ -599,22 +619,52 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
         return fail(ctx, REGK_ERR_STATE, "regk_finish: this result has no batch in flight");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    cudaError_t e = cudaEventSynchronize(slot->ev[3]);
+    cudaError_t e = cudaEventSynchronize(slot->ev[4]);
     slot->in_use = false;
     ctx->pending--;
     if (e != cudaSuccess)
         return fail(ctx, REGK_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
+    uint32_t extra_launches = 0;
+    if (slot->h_status->needs_exact && !slot->h_status->bad_bits && slot->did_path) {
+        /* Some domain has empty labels (path.join drops them): the closed-form offsets do not hold.
+           Re-run the path half with exact lengths: length kernel + last-CTA scan, then compose. */
+        if (ctx->pending)
+            return fail(ctx, REGK_ERR_STATE,
+                "batch needs the exact-offset redo but later batches are in flight; finish them in order");
+        PathParams p = slot->path_params;
+        const unsigned ntiles_r = (unsigned)((p.n + TILE - 1) / TILE);
+        CK(cudaMemsetAsync(&slot->d_status->needs_exact, 0, sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), s));
+        if (slot->path_alias)
+            regk_path_len_kernel<true><<<ntiles_r, TILE, 0, s>>>(p);
+        else
+            regk_path_len_kernel<false><<<ntiles_r, TILE, 0, s>>>(p);
+        CK(cudaGetLastError());
+        p.tile_base = p.tile_base_out;
+        if (slot->path_alias)
+            regk_path_kernel<true><<<ntiles_r, TILE, slot->path_smem, s>>>(p);
+        else
+            regk_path_kernel<false><<<ntiles_r, TILE, slot->path_smem, s>>>(p);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(slot->h_status, slot->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+        e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess)
+            return fail(ctx, REGK_ERR_CUDA, "exact-offset redo failed: %s", cudaGetErrorString(e));
+        extra_launches = 2;
+    }
     const DevStatus st = *slot->h_status;
     const uint64_t n = slot->n;
     const bool out_dev = slot->flags & REGK_OUT_DEVICE;
-    float ms_p = 0, ms_j = 0;
+    float ms_p = 0, ms_jl = 0, ms_j = 0;
     cudaEventElapsedTime(&ms_p, slot->ev[0], slot->ev[1]);
-    cudaEventElapsedTime(&ms_j, slot->ev[1], slot->ev[2]);
+    cudaEventElapsedTime(&ms_jl, slot->ev[1], slot->ev[2]);
+    cudaEventElapsedTime(&ms_j, slot->ev[2], slot->ev[3]);
     res->n = n;
     res->path_kernel_ms = ms_p;
     res->json_kernel_ms = ms_j;
-    res->kernel_ms = ms_p + ms_j;
-    res->launches = slot->launches;
+    res->json_len_kernel_ms = ms_jl;
+    res->kernel_ms = ms_p + ms_jl + ms_j;
+    res->launches = slot->launches + extra_launches;
     res->bad_bits = st.bad_bits;
     res->first_bad = st.bad_bits ? ~st.first_bad : 0;
     res->path_total = st.path_total;

@@ -53,6 +53,34 @@ RG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t shift_bits)
 #endif
 }
 
+/* right funnel shift with the shift amount clamped to 32 (shift == 32 returns hi) */
+RG_HD uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t shift_bits)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_rc(lo, hi, shift_bits);
+#else
+    return shift_bits >= 32 ? hi : (uint32_t)(((((uint64_t)hi) << 32) | lo) >> shift_bits);
+#endif
+}
+
+RG_HD uint32_t popc64(uint64_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__popcll(v);
+#else
+    return (uint32_t)__builtin_popcountll(v);
+#endif
+}
+
+RG_HD uint32_t clz64(uint64_t v)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clzll((long long)v);
+#else
+    return v ? (uint32_t)__builtin_clzll(v) : 64u;
+#endif
+}
+
 RG_HD uint32_t popc32(uint32_t v)
 {
 #if defined(__CUDA_ARCH__)
@@ -103,66 +131,65 @@ RG_HD uint32_t lower7(uint32_t v7)
 /* ---------------------------------------------------------------- sinks -- */
 
 /*
- * WordSink: sequential byte writer into a 32-bit-word buffer (shared memory on
- * the GPU).  Bytes are accumulated in a 64-bit shift register and stored as
- * aligned words; only the first and the last word of a record, which are shared
- * with the neighbouring records, are written byte by byte.
+ * WordSink: sequential byte writer into a 32-bit-word image of the tile's output
+ * (shared memory on the GPU).  Pending bytes live in a 32-bit carry; a word is
+ * stored the moment its last byte is known, so exactly one thread — the owner of
+ * the word's last byte — ever stores a given word.  Words shared by neighbouring
+ * records are resolved in two phases separated by a block barrier:
+ *   phase A  (put / put4):  full-word stores; the low bytes of a record's first word
+ *            that belong to the previous record are stored as zero;
+ *   phase B  (tail):        every record writes its last, incomplete word byte by
+ *            byte (at most 3 bytes), filling those zeros in.
+ * There is no per-store branch on "is this the first word".
  */
 struct WordSink {
-    uint32_t *words;        /* buffer base (word aligned) */
-    uint32_t wi;            /* index of the word the low bytes of acc belong to */
-    uint32_t nb;            /* bytes pending in acc, including the `head` foreign bytes */
-    uint32_t head;          /* low bytes of the first word that belong to the previous record */
-    uint64_t acc;
+    uint32_t *words;        /* image base (word aligned) */
+    uint32_t wi;            /* index of the word being filled */
+    uint32_t carry;         /* its bytes so far (low `s` bits) */
+    uint32_t s;             /* pending bits: 0, 8, 16 or 24 */
+    uint32_t wi0, h0;       /* first word and the number of foreign bytes in it */
 
     RG_HD void init(uint32_t *base, uint32_t byte_off)
     {
         words = base;
-        wi = byte_off >> 2;
-        head = byte_off & 3u;
-        nb = head;
-        acc = 0;
+        wi = wi0 = byte_off >> 2;
+        h0 = byte_off & 3u;
+        s = h0 * 8u;
+        carry = 0;
     }
-    RG_HD void flush_word()
+    RG_HD void put4(uint32_t v)
     {
-        uint32_t w = (uint32_t)acc;
-        if (head) {
-            uint8_t *b = reinterpret_cast<uint8_t *>(words + wi);
-            for (uint32_t k = head; k < 4; k++)
-                b[k] = (uint8_t)(w >> (8 * k));
-            head = 0;
-        } else {
-            words[wi] = w;
-        }
-        wi++;
-        acc >>= 32;
-        nb -= 4;
+        words[wi++] = carry | (v << s);
+        carry = funnel_rc(v, 0u, 32u - s);
     }
     /* append the low n bytes of v (1 <= n <= 4); bytes of v above n must be zero */
     RG_HD void put(uint32_t v, uint32_t n)
     {
-        acc |= (uint64_t)v << (8 * nb);
-        nb += n;
-        if (nb >= 4)
-            flush_word();
+        const uint32_t out = carry | (v << s);
+        const uint32_t ns = s + 8u * n;
+        if (ns >= 32u) {
+            words[wi++] = out;
+            carry = funnel_rc(v, 0u, 32u - s);
+            s = ns - 32u;
+        } else {
+            carry = out;
+            s = ns;
+        }
     }
-    RG_HD void put4(uint32_t v)
-    {
-        acc |= (uint64_t)v << (8 * nb);
-        nb += 4;
-        flush_word();
-    }
-    RG_HD void put1(uint32_t c)
-    {
-        put(c, 1);
-    }
-    RG_HD void finish()
+    RG_HD void put1(uint32_t c) { put(c, 1); }
+    RG_HD void finish() {}
+    /* phase B: after every thread of the tile has finished phase A */
+    RG_HD void tail()
     {
         uint8_t *b = reinterpret_cast<uint8_t *>(words + wi);
-        for (uint32_t k = head; k < nb; k++)
-            b[k] = (uint8_t)(acc >> (8 * k));
-        head = 0;
-        nb = 0;
+        const uint32_t lo = (wi == wi0) ? h0 : 0u;
+        const uint32_t hi = s >> 3;
+        if (lo <= 0u && hi > 0u)
+            b[0] = (uint8_t)carry;
+        if (lo <= 1u && hi > 1u)
+            b[1] = (uint8_t)(carry >> 8);
+        if (lo <= 2u && hi > 2u)
+            b[2] = (uint8_t)(carry >> 16);
     }
 };
 
@@ -178,6 +205,7 @@ struct ByteSink {
     RG_HD void put4(uint32_t v) { put(v, 4); }
     RG_HD void put1(uint32_t c) { *p++ = (uint8_t)c; }
     RG_HD void finish() {}
+    RG_HD void tail() {}
 };
 
 /* CountSink: length only. */
@@ -378,6 +406,182 @@ RG_HD uint32_t check_host(const Src &src, uint32_t off, uint32_t H)
     }
     bool dots = (H == 1 && first == 0x2Eu) || (H == 2 && first == 0x2E2Eu);
     return ((hibits & 0x80808080u) || hit || dots) ? (uint32_t)BAD_HOST_BYTE : 0u;
+}
+
+/* ------------------------------------------- tile-cooperative pre-pass -- */
+
+/* bits 7/15/23/31 of m -> bits 0..3 */
+RG_HD uint32_t movemask4(uint32_t m)
+{
+    return (((m >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+
+/*
+ * Domain pre-pass over the staged bytes of a tile, 16 bytes per step, thread t of
+ * nt takes chunks t, t+nt, ...: lower-cases ASCII letters in place (A1,
+ * toLowerCase), records one "is '.'" bit per byte in `bits` (16 bits per chunk) and
+ * returns nonzero if a byte outside the fence (>= 0x80 or '/') was seen anywhere in
+ * the chunks it handled — the caller then re-validates record by record.
+ */
+RG_HD uint32_t prepass_domain(uint32_t *dom_words, uint16_t *bits, uint32_t nchunks, uint32_t t, uint32_t nt)
+{
+    uint32_t hib = 0, slash = 0;
+    for (uint32_t c = t; c < nchunks; c += nt) {
+        uint32_t m = 0;
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w = dom_words[4 * c + j];
+            const uint32_t v7 = w & 0x7F7F7F7Fu;
+            const uint32_t x = v7 ^ 0x2E2E2E2Eu;                /* '.' -> 0x00, '/' -> 0x01 */
+            const uint32_t dot = zero7(x);
+            slash |= dot ^ zero7(x & 0x7E7E7E7Eu);
+            hib |= w;
+            dom_words[4 * c + j] = lower7(v7) | (w & 0x80808080u);
+            m |= movemask4(dot) << (4 * j);
+        }
+        bits[c] = (uint16_t)m;
+    }
+    return (hib & 0x80808080u) | slash;
+}
+
+/* Hostname pre-pass: nonzero if any staged byte is >= 0x80, NUL or '/'. */
+RG_HD uint32_t prepass_host(const uint32_t *host_words, uint32_t nchunks, uint32_t t, uint32_t nt)
+{
+    uint32_t hib = 0, hit = 0;
+    for (uint32_t c = t; c < nchunks; c += nt) {
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w = host_words[4 * c + j];
+            const uint32_t v7 = w & 0x7F7F7F7Fu;
+            hib |= w;
+            hit |= eq7(v7, 0x2F) | zero7(v7);
+        }
+    }
+    return (hib & 0x80808080u) | hit;
+}
+
+/* What the path needs to know about one domain, from the dot bitmap. */
+struct DomainInfo {
+    uint64_t dots;          /* bit i = byte i is '.', valid when small */
+    uint32_t nondot;
+    uint32_t labels;        /* non-empty labels */
+    bool small;             /* L <= 64: `dots` describes the whole domain */
+};
+
+RG_HD uint32_t bit_window32(const uint32_t *bits, uint32_t pos)
+{
+    return funnel_r(bits[pos >> 5], bits[(pos >> 5) + 1], pos & 31u);
+}
+
+/* bits: dot bitmap of the staged tile (readable two words past the end); b0: bit index of the domain's byte 0 */
+RG_HD DomainInfo domain_info(const uint32_t *bits, uint32_t b0, uint32_t L)
+{
+    DomainInfo di;
+    di.small = L <= 64u;
+    if (di.small) {
+        const uint32_t wi = b0 >> 5, sh = b0 & 31u;
+        const uint32_t w0 = bits[wi], w1 = bits[wi + 1], w2 = bits[wi + 2];
+        const uint64_t win = ((uint64_t)funnel_r(w1, w2, sh) << 32) | funnel_r(w0, w1, sh);
+        const uint64_t mask = L >= 64u ? ~0ull : ((1ull << L) - 1ull);
+        di.dots = win & mask;
+        const uint64_t nd = ~di.dots & mask;
+        di.nondot = popc64(nd);
+        di.labels = popc64(nd & ((di.dots << 1) | 1ull));
+    } else {
+        di.dots = 0;
+        di.nondot = 0;
+        di.labels = 0;
+        uint32_t carry = 1u, pos = b0, rem = L;
+        while (rem) {
+            const uint32_t n = rem < 32u ? rem : 32u;
+            const uint32_t mask = n >= 32u ? 0xFFFFFFFFu : ((1u << n) - 1u);
+            const uint32_t w = bit_window32(bits, pos) & mask;
+            const uint32_t nd = ~w & mask;
+            di.nondot += popc32(nd);
+            di.labels += popc32(nd & ((w << 1) | carry));
+            carry = (w >> (n - 1u)) & 1u;
+            pos += n;
+            rem -= n;
+        }
+    }
+    return di;
+}
+
+RG_HD uint32_t path_length2(const DomainInfo &di, uint32_t L, uint32_t H, bool alias)
+{
+    return alias ? L + 1u : 1u + di.nondot + di.labels + H;
+}
+
+/* plain copy (bytes already lower-cased by the pre-pass) */
+template <class Src, class Sink>
+RG_HD void copy_plain(const Src &src, uint32_t off, uint32_t len, Sink &sink)
+{
+    if (len == 0)
+        return;
+    uint32_t wi = off >> 2;
+    const uint32_t sh = (off & 3u) * 8u;
+    uint32_t lo = src.word(wi);
+    while (len >= 4) {
+        const uint32_t hi = src.word_hi(wi + 1, sh != 0 || len > 4);
+        sink.put4(funnel_r(lo, hi, sh));
+        lo = hi;
+        wi++;
+        len -= 4;
+    }
+    if (len) {
+        const uint32_t hi = src.word_hi(wi + 1, sh + 8 * len > 32);
+        sink.put(funnel_r(lo, hi, sh) & low_bytes(len), len);
+    }
+}
+
+/*
+ * Emit one znode path from pre-passed inputs (see emit_path for the semantics).
+ * Label boundaries come from the dot bitmap (one clz per label) when the domain is
+ * at most 64 bytes; longer domains fall back to scanning the bytes.  The hostname is
+ * copied word for word when it is 4-byte aligned and a multiple of 4 bytes long
+ * (36-byte UUIDs at a fixed stride always are).
+ */
+template <bool ALIAS, class DSrc, class HSrc, class Sink>
+RG_HD void emit_path2(const DSrc &dsrc, uint32_t doff, uint32_t L, const DomainInfo &di, const HSrc &hsrc,
+    uint32_t hoff, uint32_t H, Sink &sink)
+{
+    if (di.small) {
+        uint32_t e = L;                                     /* end (exclusive) of the current label, relative */
+        for (;;) {
+            const uint64_t below = e >= 64u ? di.dots : (di.dots & ((1ull << e) - 1ull));
+            const uint32_t s = 64u - clz64(below);          /* position after the last '.' below e, or 0 */
+            if (ALIAS || e > s) {
+                sink.put1('/');
+                copy_plain(dsrc, doff + s, e - s, sink);
+            }
+            if (s == 0)
+                break;
+            e = s - 1;
+        }
+    } else {
+        uint32_t e = doff + L;
+        for (;;) {
+            const int32_t dot = e > doff ? find_prev_dot(dsrc, doff, e) : (int32_t)doff - 1;
+            const uint32_t s = (uint32_t)(dot + 1);
+            if (ALIAS || e > s) {
+                sink.put1('/');
+                copy_plain(dsrc, s, e - s, sink);
+            }
+            if (s == doff)
+                break;
+            e = s - 1;
+        }
+    }
+    if (!ALIAS) {
+        sink.put1('/');
+        if (((hoff | H) & 3u) == 0) {
+            const uint32_t w0 = hoff >> 2, nw = H >> 2;
+            for (uint32_t i = 0; i < nw; i++)
+                sink.put4(hsrc.word(w0 + i));
+        } else {
+            copy_plain(hsrc, hoff, H, sink);
+        }
+    }
 }
 
 /* --------------------------------------------------- A3/A4: the payload -- */

@@ -52,32 +52,52 @@ uint32_t emul_paths(const regk_batch *b, int generic, uint8_t *out_bytes, uint64
             memcpy(shost.data(), b->host_bytes + ha0, HB1 - ha0);
         std::vector<uint32_t> len(nrec), local(nrec);
         std::vector<DomainStats> st(nrec);
+        std::vector<DomainInfo> di(nrec);
+        std::vector<uint32_t> sbits((D1 - da0) / 32 + 16, 0xC3C3C3C3u);
+        uint32_t suspicious = 0;
+        if (!generic) {
+            /* cooperative pre-pass, "threads" in a scrambled order */
+            for (uint32_t tt = 0; tt < TILE; tt++) {
+                const uint32_t t = (tt * 37u) % TILE;
+                suspicious |= prepass_domain(sdom.data(), (uint16_t *)sbits.data(), (uint32_t)((D1 - da0 + 15) >> 4), t, TILE);
+                if (!alias)
+                    suspicious |= prepass_host(shost.data(), (uint32_t)((HB1 - ha0 + 15) >> 4), t, TILE);
+            }
+        }
         uint32_t total = 0;
         for (uint32_t t = 0; t < nrec; t++) {
             const uint64_t r = r0 + t;
             const uint32_t d0 = b->domain_off[r], L = b->domain_off[r + 1] - d0;
             const uint64_t h0 = alias ? 0 : (b->host_off ? b->host_off[r] : r * b->host_stride);
             const uint32_t H = alias ? 0 : (b->host_off ? b->host_off[r + 1] - b->host_off[r] : b->host_stride);
-            uint32_t bad;
+            uint32_t bad = 0;
             if (generic) {
                 GuardedWords ds{(const uint32_t *)b->domain_bytes}, hs{(const uint32_t *)b->host_bytes};
                 st[t] = scan_domain(ds, d0, L);
                 bad = st[t].bad | (alias ? 0 : check_host(hs, (uint32_t)h0, H));
+                len[t] = path_length(st[t], L, H, alias);
             } else {
                 PaddedWords ds{sdom.data()}, hs{shost.data()};
-                st[t] = scan_domain(ds, (uint32_t)(d0 - da0), L);
-                bad = st[t].bad | (alias ? 0 : check_host(hs, (uint32_t)(h0 - ha0), H));
+                di[t] = domain_info(sbits.data(), (uint32_t)(d0 - da0), L);
+                if (suspicious) {
+                    bad = scan_domain(ds, (uint32_t)(d0 - da0), L).bad;
+                    if (!alias)
+                        bad |= check_host(hs, (uint32_t)(h0 - ha0), H);
+                } else if (!alias && H <= 2) {
+                    bad = check_host(hs, (uint32_t)(h0 - ha0), H);
+                }
+                len[t] = path_length2(di[t], L, H, alias);
             }
             if (bad) {
                 bad_all |= bad;
                 fb = std::min<uint64_t>(fb, r);
             }
-            len[t] = path_length(st[t], L, H, alias);
             local[t] = total;
             total += len[t];
         }
         const uint32_t shift = (uint32_t)(base & 15);
         std::vector<uint32_t> sout((shift + total) / 4 + 16, 0xEEEEEEEEu);
+        std::vector<WordSink> sinks(nrec);
         /* compose in reverse thread order: neighbours must not clobber shared words */
         for (uint32_t tt = nrec; tt-- > 0;) {
             const uint64_t r = r0 + tt;
@@ -97,15 +117,17 @@ uint32_t emul_paths(const regk_batch *b, int generic, uint8_t *out_bytes, uint64
                     abort();
             } else {
                 PaddedWords ds{sdom.data()}, hs{shost.data()};
-                WordSink sink;
+                WordSink &sink = sinks[tt];
                 sink.init(sout.data(), local[tt] + shift);
                 if (alias)
-                    emit_path<true>(ds, (uint32_t)(d0 - da0), L, hs, (uint32_t)(h0 - ha0), H, sink);
+                    emit_path2<true>(ds, (uint32_t)(d0 - da0), L, di[tt], hs, (uint32_t)(h0 - ha0), H, sink);
                 else
-                    emit_path<false>(ds, (uint32_t)(d0 - da0), L, hs, (uint32_t)(h0 - ha0), H, sink);
-                sink.finish();
+                    emit_path2<false>(ds, (uint32_t)(d0 - da0), L, di[tt], hs, (uint32_t)(h0 - ha0), H, sink);
             }
         }
+        if (!generic)
+            for (uint32_t tt = 0; tt < nrec; tt++)     /* phase B after the "barrier" */
+                sinks[tt].tail();
         if (!generic)
             memcpy(out_bytes + base, (const uint8_t *)sout.data() + shift, total);
         base += total;
@@ -200,6 +222,7 @@ uint32_t emul_jsons(const regk_batch *b, const uint8_t *blob, uint32_t ntypes, i
         }
         const uint32_t shift = (uint32_t)(base & 15);
         std::vector<uint32_t> sout((shift + total) / 4 + 16, 0xEEEEEEEEu);
+        std::vector<WordSink> sinks(nrec);
         for (uint32_t tt = nrec; tt-- > 0;) {
             const uint64_t r = r0 + tt;
             Rec &q = rec[tt];
@@ -213,14 +236,16 @@ uint32_t emul_jsons(const regk_batch *b, const uint8_t *blob, uint32_t ntypes, i
                 if ((uint64_t)(sink.p - (out_bytes + base + q.local)) != q.len)
                     abort();
             } else {
-                WordSink sink;
+                WordSink &sink = sinks[tt];
                 sink.init(sout.data(), q.local + shift);
                 emit_json(fsrc, q.tf, q.aw, asrc, q.a0, q.al, q.has_ttl, q.ttl, q.has_ports, q.k, port, sink);
-                sink.finish();
             }
         }
-        if (!generic)
+        if (!generic) {
+            for (uint32_t tt = 0; tt < nrec; tt++)
+                sinks[tt].tail();
             memcpy(out_bytes + base, (const uint8_t *)sout.data() + shift, total);
+        }
         base += total;
     }
     out_off[n] = base;

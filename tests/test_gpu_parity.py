@@ -51,7 +51,7 @@ def test_config2_full_size(ctx):
     batch = synth.generate("config2")
     got = ctx.register_batch(batch)
     assert_same(got, oracle.register_batch(batch))
-    assert got.launches == 2
+    assert got.launches == 3          # path, payload lengths, payload
 
 
 @pytest.mark.parametrize("start", [1, 7, 255, 1001, 99_999_999_000])
@@ -113,7 +113,7 @@ def test_paths_only_and_payloads_only(ctx):
     got = ctx.register_batch(batch, payloads=False)
     assert np.array_equal(got.path_bytes, want.path_bytes) and got.launches == 1
     got = ctx.register_batch(batch, paths=False)
-    assert np.array_equal(got.json_bytes, want.json_bytes) and got.launches == 1
+    assert np.array_equal(got.json_bytes, want.json_bytes) and got.launches == 2
 
 
 def test_known_answers(ctx):
@@ -202,3 +202,34 @@ def test_golden_fixtures_from_the_executed_reference(ctx, name):
     for i, row in enumerate(rows):
         assert got.path(i) == row["path"].encode("latin-1"), (i, row["in"])
         assert got.json(i) == row["json"].encode("utf-8"), (i, row["in"])
+
+
+def test_empty_labels_take_the_exact_offset_redo(ctx):
+    # closed-form path offsets hold only without empty labels; one such record anywhere forces the exact pass
+    recs = [{"domain": b"svc%d.example.com" % i, "hostname": b"h%03d" % i, "type": b"host", "address": b"10.0.0.1"}
+            for i in range(1000)]
+    clean = ctx.register_batch(RecordBatch.from_records(recs))
+    assert clean.launches == 3
+    recs[777]["domain"] = b"a..b"
+    batch = RecordBatch.from_records(recs)
+    got = ctx.register_batch(batch)
+    assert got.launches == 5          # + exact length kernel + second compose
+    assert_same(got, oracle.register_batch(batch))
+    assert got.path(777) == b"/b/a/h777"
+
+
+def test_corrupt_offsets_are_refused_not_dereferenced(ctx):
+    from registrar_b200._native import OutOfDomainError
+    from registrar_b200.batch import BAD_TOO_LARGE
+    batch = synth.generate("config3", n=2000)
+    for field, idx, val in [("domain_off", 700, 5), ("domain_off", 700, 2 ** 31), ("addr_off", 1200, 2 ** 30),
+                            ("ports_off", 1500, 2 ** 29)]:
+        arr = getattr(batch, field).copy()
+        saved = getattr(batch, field)
+        arr[idx] = val
+        setattr(batch, field, arr)
+        with pytest.raises(OutOfDomainError) as ei:
+            ctx.register_batch(batch)
+        assert ei.value.result.bad_bits & BAD_TOO_LARGE
+        setattr(batch, field, saved)
+    assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
