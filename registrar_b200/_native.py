@@ -17,7 +17,7 @@ from .batch import (FLAG_IN_DEVICE, FLAG_NODE_ALIAS, FLAG_NO_JSON, FLAG_NO_PATH,
                     RecordBatch)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libregk.so")
+LIB_PATH = os.environ.get("REGK_LIB") or os.path.join(_HERE, "libregk.so")      # REGK_LIB: A/B builds (dev)
 
 REGK_OK = 0
 REGK_ERR_INVALID_ARG = 1

@@ -469,19 +469,19 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         (rc = ensure_dev(ctx, ctx->json_bytes, json_cap)) || (rc = ensure_dev(ctx, ctx->json_off, (n + 1) * 8)))
         return rc;
 
-    /* ---- workspace: status | counters | per-tile totals and bases of both kernels ---- */
+    /* ---- workspace: status | two-level byte totals of both halves (zeroed with the status) ---- */
     const uint64_t ntiles = (n + TILE - 1) / TILE;
+    const uint64_t nsuper = ntiles / SUPER + 1;
     const size_t totals_p_off = 128;
-    const size_t bases_p_off = (totals_p_off + ntiles * 4 + 15) & ~(size_t)15;
-    const size_t totals_j_off = bases_p_off + (ntiles + 1) * 8;
-    const size_t bases_j_off = (totals_j_off + ntiles * 4 + 15) & ~(size_t)15;
-    const size_t work_bytes = bases_j_off + (ntiles + 1) * 8 + 64;
+    const size_t super_p_off = (totals_p_off + ntiles * 4 + 15) & ~(size_t)15;
+    const size_t totals_j_off = super_p_off + nsuper * 8;
+    const size_t super_j_off = (totals_j_off + ntiles * 4 + 15) & ~(size_t)15;
+    const size_t work_bytes = super_j_off + nsuper * 8 + 64;
     if ((rc = ensure_dev(ctx, ctx->work, work_bytes)))
         return rc;
     uint8_t *wk = (uint8_t *)ctx->work.p;
-    CK(cudaMemsetAsync(wk, 0, 128, s));
+    CK(cudaMemsetAsync(wk, 0, work_bytes, s));
     DevStatus *d_status = (DevStatus *)wk;
-    uint32_t *counters = (uint32_t *)(wk + 64);
 
     if (n == 0) {
         CK(cudaMemsetAsync(ctx->path_off.p, 0, 8, s));
@@ -491,6 +491,47 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     const uint32_t force_generic = (uint32_t)opt_get(ctx, "force_generic", 0);
     slot.did_path = false;
     slot.d_status = d_status;
+    /* payload parameters first: when both halves run, the path kernel also produces the payload tile bases */
+    JsonParams jp{};
+    size_t json_smem = 0;
+    if (n && do_json) {
+        jp.n = n;
+        jp.type_id = (const uint8_t *)dev[4];
+        jp.addr_bytes = (const uint8_t *)dev[5];
+        jp.addr_off = (const uint32_t *)dev[6];
+        jp.ttl = (const int32_t *)dev[7];
+        jp.ports_off = (const uint32_t *)dev[8];
+        jp.ports = (const uint32_t *)dev[9];
+        jp.ports_present = (const uint8_t *)dev[10];
+        jp.frag_blob = (const uint8_t *)ctx->blob_dev.p;
+        jp.ntypes = (uint32_t)ctx->types.size();
+        jp.blob_bytes = (uint32_t)ctx->blob_host.size();
+        jp.out_bytes = (uint8_t *)ctx->json_bytes.p;
+        jp.out_off = (unsigned long long *)ctx->json_off.p;
+        jp.out_capacity = json_cap;
+        jp.tile_total = (uint32_t *)(wk + totals_j_off);
+        jp.super_total = (unsigned long long *)(wk + super_j_off);
+        jp.status = d_status;
+        jp.addr_limit = addr_len;
+        jp.ports_limit = ports_len;
+        jp.force_generic = force_generic;
+        uint32_t out_cap = (uint32_t)opt_get(ctx, "json_out_cap", 0);
+        if (!out_cap) {
+            /* mean payload estimate: fixed keys + type twice + address twice + ttl + ports */
+            const uint64_t mean = 42 + 2ull * ctx->max_type_q + (n ? 2 * addr_len / n : 0) + 11 +
+                (ports_len ? 11 + (n ? 6 * ports_len / n : 0) : 0) + 2;
+            out_cap = (uint32_t)std::min<uint64_t>(align16(mean * TILE * 9 / 8 + 512), 98304);
+        }
+        out_cap = (uint32_t)align16(out_cap);
+        jp.out_cap = out_cap;
+        json_smem = (size_t)jp.blob_bytes + out_cap + 32;
+        if (json_smem > (size_t)ctx->max_smem_optin)
+            return fail(ctx, REGK_ERR_INVALID_ARG, "json kernel needs %zu B of shared memory (> %d)", json_smem, ctx->max_smem_optin);
+    }
+    const bool fused_len = n && do_path && do_json;
+    JsonParams jp_side{};
+    if (fused_len)
+        jp_side = jp;
     CK(cudaEventRecord(slot.ev[0], s));
     if (n && do_path) {
         PathParams p{};
@@ -503,10 +544,9 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         p.out_bytes = (uint8_t *)ctx->path_bytes.p;
         p.out_off = (unsigned long long *)ctx->path_off.p;
         p.out_capacity = path_cap;
-        p.tile_base = nullptr;                  /* closed-form offsets; see regk_finish for the exact redo */
+        p.exact = 0;                            /* closed-form offsets; see regk_finish for the exact redo */
         p.tile_total = (uint32_t *)(wk + totals_p_off);
-        p.tile_base_out = (unsigned long long *)(wk + bases_p_off);
-        p.counter = counters + 0;
+        p.super_total = (unsigned long long *)(wk + super_p_off);
         p.status = d_status;
         p.dom_limit = dom_len;
         p.host_limit = host_len;
@@ -515,7 +555,7 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         const uint64_t mean_dom_tile = dom_len / std::max<uint64_t>(ntiles, 1) + 1;
         uint32_t dom_cap = (uint32_t)opt_get(ctx, "dom_cap", 0);
         if (!dom_cap)
-            dom_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(align16(mean_dom_tile * 3 / 2 + 512), 4096), 49152);
+            dom_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(align16(mean_dom_tile * 5 / 4 + 384), 2048), 49152);
         dom_cap = (uint32_t)((dom_cap + 127) & ~127u);         /* bitmap region stays 16-byte aligned */
         uint32_t host_cap = 0;
         if (!alias) {
@@ -532,10 +572,10 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         p.out_cap = out_cap;
         if (alias) {
             CK(cudaFuncSetAttribute(regk_path_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            regk_path_kernel<true><<<(unsigned)ntiles, TILE, smem, s>>>(p);
+            regk_path_kernel<true><<<(unsigned)ntiles, TILE, smem, s>>>(p, jp_side);
         } else {
             CK(cudaFuncSetAttribute(regk_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            regk_path_kernel<false><<<(unsigned)ntiles, TILE, smem, s>>>(p);
+            regk_path_kernel<false><<<(unsigned)ntiles, TILE, smem, s>>>(p, jp_side);
         }
         CK(cudaGetLastError());
         launches++;
@@ -546,46 +586,15 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     }
     CK(cudaEventRecord(slot.ev[1], s));
     if (n && do_json) {
-        JsonParams p{};
-        p.n = n;
-        p.type_id = (const uint8_t *)dev[4];
-        p.addr_bytes = (const uint8_t *)dev[5];
-        p.addr_off = (const uint32_t *)dev[6];
-        p.ttl = (const int32_t *)dev[7];
-        p.ports_off = (const uint32_t *)dev[8];
-        p.ports = (const uint32_t *)dev[9];
-        p.ports_present = (const uint8_t *)dev[10];
-        p.frag_blob = (const uint8_t *)ctx->blob_dev.p;
-        p.ntypes = (uint32_t)ctx->types.size();
-        p.blob_bytes = (uint32_t)ctx->blob_host.size();
-        p.out_bytes = (uint8_t *)ctx->json_bytes.p;
-        p.out_off = (unsigned long long *)ctx->json_off.p;
-        p.out_capacity = json_cap;
-        p.tile_total = (uint32_t *)(wk + totals_j_off);
-        p.tile_base = (unsigned long long *)(wk + bases_j_off);
-        p.counter = counters + 1;
-        p.status = d_status;
-        p.addr_limit = addr_len;
-        p.ports_limit = ports_len;
-        p.force_generic = force_generic;
-        uint32_t out_cap = (uint32_t)opt_get(ctx, "json_out_cap", 0);
-        if (!out_cap) {
-            /* mean payload estimate: fixed keys + type twice + address twice + ttl + ports */
-            const uint64_t mean = 42 + 2ull * ctx->max_type_q + (n ? 2 * addr_len / n : 0) + 11 +
-                (ports_len ? 11 + (n ? 6 * ports_len / n : 0) : 0) + 2;
-            out_cap = (uint32_t)std::min<uint64_t>(align16(mean * TILE * 5 / 4 + 1024), 98304);
+        if (!fused_len) {
+            const unsigned len_grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 8);
+            regk_json_len_kernel<<<len_grid, TILE, 0, s>>>(jp, (uint32_t)ntiles);
+            CK(cudaGetLastError());
+            launches++;
         }
-        out_cap = (uint32_t)align16(out_cap);
-        p.out_cap = out_cap;
-        size_t smem = (size_t)p.blob_bytes + out_cap + 32;
-        if (smem > (size_t)ctx->max_smem_optin)
-            return fail(ctx, REGK_ERR_INVALID_ARG, "json kernel needs %zu B of shared memory (> %d)", smem, ctx->max_smem_optin);
-        regk_json_len_kernel<<<(unsigned)ntiles, TILE, 0, s>>>(p);
-        CK(cudaGetLastError());
-        launches++;
         CK(cudaEventRecord(slot.ev[2], s));
-        CK(cudaFuncSetAttribute(regk_json_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        regk_json_kernel<<<(unsigned)ntiles, TILE, smem, s>>>(p);
+        CK(cudaFuncSetAttribute(regk_json_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)json_smem));
+        regk_json_kernel<<<(unsigned)ntiles, TILE, json_smem, s>>>(jp);
         CK(cudaGetLastError());
         launches++;
     } else {
@@ -634,17 +643,17 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
         PathParams p = slot->path_params;
         const unsigned ntiles_r = (unsigned)((p.n + TILE - 1) / TILE);
         CK(cudaMemsetAsync(&slot->d_status->needs_exact, 0, sizeof(uint32_t), s));
-        CK(cudaMemsetAsync(p.counter, 0, sizeof(uint32_t), s));
+        /* the path totals were zeroed with the workspace and nothing has touched them yet */
         if (slot->path_alias)
             regk_path_len_kernel<true><<<ntiles_r, TILE, 0, s>>>(p);
         else
             regk_path_len_kernel<false><<<ntiles_r, TILE, 0, s>>>(p);
         CK(cudaGetLastError());
-        p.tile_base = p.tile_base_out;
+        p.exact = 1;
         if (slot->path_alias)
-            regk_path_kernel<true><<<ntiles_r, TILE, slot->path_smem, s>>>(p);
+            regk_path_kernel<true><<<ntiles_r, TILE, slot->path_smem, s>>>(p, JsonParams{});
         else
-            regk_path_kernel<false><<<ntiles_r, TILE, slot->path_smem, s>>>(p);
+            regk_path_kernel<false><<<ntiles_r, TILE, slot->path_smem, s>>>(p, JsonParams{});
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(slot->h_status, slot->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
         e = cudaStreamSynchronize(s);

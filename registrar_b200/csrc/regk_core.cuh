@@ -576,8 +576,18 @@ RG_HD void emit_path2(const DSrc &dsrc, uint32_t doff, uint32_t L, const DomainI
         sink.put1('/');
         if (((hoff | H) & 3u) == 0) {
             const uint32_t w0 = hoff >> 2, nw = H >> 2;
-            for (uint32_t i = 0; i < nw; i++)
-                sink.put4(hsrc.word(w0 + i));
+            if (nw == 9) {                                  /* 36-byte UUID: all loads in flight, then the stores */
+                uint32_t h[9];
+                #pragma unroll
+                for (int i = 0; i < 9; i++)
+                    h[i] = hsrc.word(w0 + i);
+                #pragma unroll
+                for (int i = 0; i < 9; i++)
+                    sink.put4(h[i]);
+            } else {
+                for (uint32_t i = 0; i < nw; i++)
+                    sink.put4(hsrc.word(w0 + i));
+            }
         } else {
             copy_plain(hsrc, hoff, H, sink);
         }
@@ -667,8 +677,15 @@ RG_HD uint32_t addr_word_bad(uint32_t v, uint32_t keep)
  * Fragments start on word boundaries inside `blob`.
  */
 struct TypeFrag {
-    uint16_t f1_off, f1_len, f2_off, f2_len;                /* byte offsets into the blob */
+    uint16_t f1_off, f1_len, f2_off, f2_len;                /* byte offsets into the blob (word aligned) */
 };
+/* Each fragment is stored as 4 pre-shifted variants, back to back, variant k = k zero bytes + the fragment,
+ * zero padded to frag_stride_words(len) words: appending it at byte phase k of the output is then a plain
+ * word copy (first word OR-ed with the pending bytes) instead of a shift per word. */
+RG_HD uint32_t frag_stride_words(uint32_t len)
+{
+    return (len + 6u) >> 2;                                 /* ceil((len + 3) / 4) */
+}
 
 template <class Src, class Sink>
 RG_HD void put_aligned(const Src &blob, uint32_t off, uint32_t len, Sink &sink)
@@ -680,6 +697,79 @@ RG_HD void put_aligned(const Src &blob, uint32_t off, uint32_t len, Sink &sink)
     }
     if (len)
         sink.put(blob.word(wi) & low_bytes(len), len);
+}
+
+/* generic sinks: the unshifted variant */
+template <class Src, class Sink>
+RG_HD void put_frag(const Src &blob, uint32_t off, uint32_t len, Sink &sink)
+{
+    put_aligned(blob, off, len, sink);
+}
+
+/* word sink: copy from the variant that matches the sink's byte phase */
+template <class Src>
+RG_HD void put_frag(const Src &blob, uint32_t off, uint32_t len, WordSink &sink)
+{
+    const uint32_t ph = sink.s >> 3;
+    const uint32_t src = (off >> 2) + ph * frag_stride_words(len);
+    const uint32_t total = ph + len;
+    const uint32_t nfull = total >> 2, rem = total & 3u;
+    const uint32_t first = blob.word(src) | sink.carry;
+    if (nfull == 0) {
+        sink.carry = first;
+        sink.s = total * 8u;
+        return;
+    }
+    uint32_t *dst = sink.words + sink.wi;
+    dst[0] = first;
+    uint32_t i = 1;
+    for (; i + 4 <= nfull; i += 4) {                        /* loads first: 4 independent LDS in flight */
+        const uint32_t a = blob.word(src + i), b = blob.word(src + i + 1), c = blob.word(src + i + 2),
+                       d = blob.word(src + i + 3);
+        dst[i] = a;
+        dst[i + 1] = b;
+        dst[i + 2] = c;
+        dst[i + 3] = d;
+    }
+    for (; i < nfull; i++)
+        dst[i] = blob.word(src + i);
+    sink.wi += nfull;
+    sink.carry = rem ? blob.word(src + nfull) : 0u;
+    sink.s = rem * 8u;
+}
+
+/* the first (up to) 16 address bytes, from registers (bytes of aw[] beyond n are zero) */
+template <class Sink>
+RG_HD void put_addr16(const uint32_t (&aw)[4], uint32_t n, Sink &sink)
+{
+    #pragma unroll
+    for (int w = 0; w < 4; w++) {
+        if (n >= 4u * (w + 1))
+            sink.put4(aw[w]);
+        else if (n > 4u * w)
+            sink.put(aw[w], n - 4u * w);
+    }
+}
+
+/* word sink: shift the whole 16-byte register block once, then store what is complete */
+RG_HD void put_addr16(const uint32_t (&aw)[4], uint32_t n, WordSink &sink)
+{
+    const uint32_t sh = sink.s, back = 32u - sh;
+    const uint32_t o0 = sink.carry | (aw[0] << sh);
+    const uint32_t o1 = funnel_rc(aw[0], aw[1], back);
+    const uint32_t o2 = funnel_rc(aw[1], aw[2], back);
+    const uint32_t o3 = funnel_rc(aw[2], aw[3], back);
+    const uint32_t o4 = funnel_rc(aw[3], 0u, back);
+    const uint32_t total = (sh >> 3) + n;
+    const uint32_t nfull = total >> 2;                      /* 0..4 */
+    uint32_t *dst = sink.words + sink.wi;
+    if (nfull > 0) dst[0] = o0;
+    if (nfull > 1) dst[1] = o1;
+    if (nfull > 2) dst[2] = o2;
+    if (nfull > 3) dst[3] = o3;
+    sink.carry = nfull == 0 ? o0 : nfull == 1 ? o1 : nfull == 2 ? o2 : nfull == 3 ? o3 : o4;
+    sink.wi += nfull;
+    sink.s = (total & 3u) * 8u;
 }
 
 RG_HD uint32_t json_length(uint32_t f1_len, uint32_t f2_len, uint32_t al, bool has_ttl, int32_t ttl,
@@ -697,19 +787,6 @@ RG_HD uint32_t json_length(uint32_t f1_len, uint32_t f2_len, uint32_t al, bool h
 #define RG_LE4(a, b, c, d) ((uint32_t)(uint8_t)(a) | ((uint32_t)(uint8_t)(b) << 8) | \
     ((uint32_t)(uint8_t)(c) << 16) | ((uint32_t)(uint8_t)(d) << 24))
 
-/* the first (up to) 16 address bytes, from registers */
-template <class Sink>
-RG_HD void put_addr16(const uint32_t (&aw)[4], uint32_t n, Sink &sink)
-{
-    #pragma unroll
-    for (int w = 0; w < 4; w++) {
-        if (n >= 4u * (w + 1))
-            sink.put4(aw[w]);
-        else if (n > 4u * w)
-            sink.put(aw[w] & low_bytes(n - 4u * w), n - 4u * w);
-    }
-}
-
 /*
  * Emit the JSON payload of one host record (A3 + A4):
  *   {"type":"T","address":"A"[,"ttl":N],"T":{"address":"A"[,"ports":[p,...]]}}
@@ -723,7 +800,7 @@ RG_HD void emit_json(const FSrc &blob, const TypeFrag &tf, const uint32_t (&aw)[
     Sink &sink)
 {
     const uint32_t a16 = al < 16u ? al : 16u;
-    put_aligned(blob, tf.f1_off, tf.f1_len, sink);          /* {"type":"T","address":" */
+    put_frag(blob, tf.f1_off, tf.f1_len, sink);             /* {"type":"T","address":" */
     put_addr16(aw, a16, sink);
     if (al > 16u)
         copy_bytes<false>(asrc, aoff + 16u, al - 16u, sink);
@@ -734,7 +811,7 @@ RG_HD void emit_json(const FSrc &blob, const TypeFrag &tf, const uint32_t (&aw)[
     } else {
         sink.put1('"');
     }
-    put_aligned(blob, tf.f2_off, tf.f2_len, sink);          /* ,"T":{"address":" */
+    put_frag(blob, tf.f2_off, tf.f2_len, sink);             /* ,"T":{"address":" */
     put_addr16(aw, a16, sink);
     if (al > 16u)
         copy_bytes<false>(asrc, aoff + 16u, al - 16u, sink);

@@ -41,7 +41,16 @@
 
 namespace regk {
 
-constexpr int TILE = 256;                       /* records per tile == threads per CTA */
+#ifndef REGK_TILE
+#define REGK_TILE 256
+#endif
+#ifndef REGK_MINB_PATH
+#define REGK_MINB_PATH 5
+#endif
+#ifndef REGK_MINB_JSON
+#define REGK_MINB_JSON 5
+#endif
+constexpr int TILE = REGK_TILE;                 /* records per tile == threads per CTA */
 constexpr int WARPS = TILE / 32;
 
 /* device-side run status, copied to the host after the kernels */
@@ -93,22 +102,43 @@ __device__ __forceinline__ void stage_in(uint8_t *smem, const uint8_t *src, uint
 /*
  * Flush the shared-memory image of the tile's output range to global memory.
  * smem byte i corresponds to global byte (gbase & ~15) + i; valid bytes are
- * [gbase, gbase + total).
+ * [gbase, gbase + total).  The 16-byte-aligned body goes out as ONE bulk
+ * asynchronous copy (cp.async.bulk shared::cta -> global, the TMA engine; SASS
+ * UBLKCP) issued by a single thread; the < 16-byte head and tail are stored
+ * byte-wise by 32 threads.  Callers must have executed fence_proxy_async() after
+ * their shared-memory writes and a block barrier before calling.
  */
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 __device__ __forceinline__ void flush_out(uint8_t *gout, const uint8_t *smem, uint64_t gbase, uint32_t total)
 {
     const uint64_t a0 = gbase & ~15ull;
     const uint32_t lo = (uint32_t)(gbase - a0);
     const uint32_t hi = lo + total;
-    for (uint32_t c = 16u * threadIdx.x; c < hi; c += 16u * TILE) {
-        if (c >= lo && c + 16 <= hi) {
-            stg_v4(gout + a0 + c, *reinterpret_cast<const uint4 *>(smem + c));
-        } else {
-            for (uint32_t k = 0; k < 16; k++)
-                if (c + k >= lo && c + k < hi)
-                    gout[a0 + c + k] = smem[c + k];
-        }
+    uint32_t body_lo = (lo + 15u) & ~15u, body_hi = hi & ~15u;
+    if (body_hi <= body_lo)
+        body_lo = body_hi = hi;                 /* nothing aligned: everything is "head" */
+    const uint32_t t = threadIdx.x;
+    if (t == 0 && body_hi > body_lo) {
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(smem + body_lo);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(gout + a0 + body_lo), "r"(src), "r"(body_hi - body_lo) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    if (t >= 32 && t < 48) {
+        const uint32_t i = lo + (t - 32);
+        if (i < body_lo)
+            gout[a0 + i] = smem[i];
+    } else if (t >= 64 && t < 80) {
+        const uint32_t i = body_hi + (t - 64);
+        if (i < hi)
+            gout[a0 + i] = smem[i];
+    }
+    if (t == 0 && body_hi > body_lo)            /* shared memory must stay alive until the engine has read it */
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 /* Block-wide exclusive scan of one value per thread (two barriers). */
@@ -140,36 +170,39 @@ __device__ __forceinline__ T block_scan(T *warp_sum /* smem[WARPS] */, T v, T *t
 }
 
 /*
- * Called by every CTA of a length kernel after it has stored totals[blockIdx.x]:
- * the CTA that arrives last scans the per-tile totals into exclusive per-tile bases
- * (bases[ntiles] = grand total).  One CTA, coalesced, a few microseconds for 10^5 tiles.
+ * Two-level totals instead of a scan pass: producers add each warp's byte count into tile_total[tile]
+ * (u32) and super_total[tile / SUPER] (u64) with atomics; a consumer CTA derives its own exclusive base
+ * as  sum(super_total[0 .. tile/SUPER)) + sum(tile_total[SUPER*(tile/SUPER) .. tile))  — at most
+ * ntiles/SUPER + SUPER - 1 loads, done by warp 0 while the other warps load their records' metadata.
+ * Kernel boundaries are the only synchronisation.  (Tried and dropped, with measurements in DESIGN.md:
+ * a chained look-back scan, a fence + last-CTA scan, a separate single-CTA scan kernel.)
  */
-__device__ __forceinline__ void finalize_bases(const uint32_t *totals, unsigned long long *bases, uint32_t ntiles,
-    uint32_t *counter)
+constexpr uint32_t SUPER = 64;
+
+__device__ __forceinline__ void add_tile_total(uint32_t *tile_total, unsigned long long *super_total, uint32_t tile,
+    uint32_t warp_bytes)
 {
-    __shared__ unsigned long long fb_warp[WARPS];
-    __shared__ uint32_t fb_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0)
-        fb_last = (atomicAdd(counter, 1u) == gridDim.x - 1u);
-    __syncthreads();
-    if (!fb_last)
-        return;
-    __threadfence();
-    const uint32_t chunk = (ntiles + TILE - 1) / TILE;
-    const uint32_t lo = min(threadIdx.x * chunk, ntiles), hi = min(lo + chunk, ntiles);
-    unsigned long long sum = 0;
-    for (uint32_t i = lo; i < hi; i++)
-        sum += __ldcg(totals + i);
-    unsigned long long all;
-    unsigned long long run = block_scan<unsigned long long>(fb_warp, sum, &all);
-    for (uint32_t i = lo; i < hi; i++) {
-        bases[i] = run;
-        run += __ldcg(totals + i);
+    if (warp_bytes) {
+        atomicAdd(tile_total + tile, warp_bytes);
+        atomicAdd(super_total + tile / SUPER, (unsigned long long)warp_bytes);
     }
-    if (threadIdx.x == 0)
-        bases[ntiles] = all;
+}
+
+/* call from warp 0 (all 32 lanes); every lane returns the tile's exclusive base */
+__device__ __forceinline__ unsigned long long tile_base_from_totals(const uint32_t *tile_total,
+    const unsigned long long *super_total, uint32_t tile)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nsuper = tile / SUPER;
+    unsigned long long acc = 0;
+    for (uint32_t i = lane; i < nsuper; i += 32)
+        acc += super_total[i];
+    for (uint32_t i = nsuper * SUPER + lane; i < tile; i += 32)
+        acc += tile_total[i];
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    return acc;
 }
 
 __device__ __forceinline__ void report_bad(DevStatus *st, uint32_t bad, uint64_t rec)
@@ -180,245 +213,7 @@ __device__ __forceinline__ void report_bad(DevStatus *st, uint32_t bad, uint64_t
     }
 }
 
-/* ================================================================ paths == */
-
-struct PathParams {
-    uint64_t n;
-    const uint8_t *domain_bytes;
-    const uint32_t *domain_off;
-    const uint8_t *host_bytes;
-    const uint32_t *host_off;           /* NULL: fixed stride */
-    uint32_t host_stride;
-    uint8_t *out_bytes;
-    unsigned long long *out_off;        /* [n+1] */
-    uint64_t out_capacity;
-    const unsigned long long *tile_base;        /* [ntiles+1] exact bases, or NULL: closed-form offsets */
-    uint32_t *tile_total;               /* length kernel only: [ntiles] */
-    unsigned long long *tile_base_out;  /* length kernel only: [ntiles+1] */
-    uint32_t *counter;                  /* length kernel only */
-    DevStatus *status;
-    uint64_t dom_limit, host_limit;     /* bytes behind domain_bytes / host_bytes (trusted, from the caller) */
-    uint32_t dom_cap, host_cap, out_cap;        /* shared-memory budgets in bytes */
-    uint32_t force_generic;
-};
-
-/* closed-form offset of record r's path when no label is empty: path_len = L + 2 + H (alias: L + 1) */
-template <bool ALIAS>
-__device__ __forceinline__ unsigned long long path_cf(const PathParams &p, uint64_t r)
-{
-    unsigned long long v = (unsigned long long)p.domain_off[r];
-    if (ALIAS)
-        return v + r;
-    return v + 2ull * r + (p.host_off ? (unsigned long long)p.host_off[r] : r * (unsigned long long)p.host_stride);
-}
-
-/*
- * Exact path lengths -> per-tile totals -> per-tile bases.  Only launched when the compose
- * kernel reported `needs_exact` (some domain has empty labels, which path.join drops).
- */
-template <bool ALIAS>
-__global__ void __launch_bounds__(TILE) regk_path_len_kernel(const PathParams p)
-{
-    __shared__ uint32_t warp_sum[WARPS];
-    const uint32_t tile = blockIdx.x, t = threadIdx.x;
-    const uint64_t r0 = (uint64_t)tile * TILE;
-    const uint32_t nrec = (uint32_t)min((uint64_t)TILE, p.n - r0);
-    uint32_t len = 0;
-    if (t < nrec) {
-        const uint64_t r = r0 + t;
-        const uint32_t d0 = p.domain_off[r], d1 = p.domain_off[r + 1];
-        const uint32_t L = (d1 >= d0 && d1 <= p.dom_limit) ? d1 - d0 : 0;   /* corrupt offsets: flagged by the compose kernel */
-        uint32_t H = 0;
-        if (!ALIAS) {
-            if (p.host_off) {
-                const uint32_t a = p.host_off[r], b = p.host_off[r + 1];
-                H = b >= a ? b - a : 0;
-            } else {
-                H = p.host_stride;
-            }
-        }
-        const GuardedWords dsrc{reinterpret_cast<const uint32_t *>(p.domain_bytes)};
-        len = path_length(scan_domain(dsrc, d0, L), L, H, ALIAS);
-    }
-    uint32_t total;
-    block_scan<uint32_t>(warp_sum, len, &total);
-    if (t == 0)
-        p.tile_total[tile] = total;
-    finalize_bases(p.tile_total, p.tile_base_out, gridDim.x, p.counter);
-}
-
-template <bool ALIAS>
-__global__ void __launch_bounds__(TILE, 3) regk_path_kernel(const PathParams p)
-{
-    extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint32_t warp_sum[WARPS];
-    uint8_t *s_dom = smem;                                      /* staged domain bytes, lower-cased in place */
-    uint8_t *s_bits = s_dom + p.dom_cap + 32;                   /* 1 bit per staged domain byte: is '.' */
-    uint8_t *s_host = s_bits + p.dom_cap / 8 + 16;
-    uint8_t *s_out = s_host + (ALIAS ? 0 : p.host_cap + 32);
-
-    const uint32_t tile = blockIdx.x;
-    const uint64_t r0 = (uint64_t)tile * TILE;
-    const uint32_t nrec = (uint32_t)min((uint64_t)TILE, p.n - r0);
-    const uint32_t t = threadIdx.x;
-    const bool live = t < nrec;
-    const uint64_t r = r0 + (live ? t : 0);
-    const bool exact = p.tile_base != nullptr;
-
-    /* per-record extents */
-    uint32_t d0 = p.domain_off[r], d1 = p.domain_off[r + 1];
-    uint32_t bad = 0;
-    if (d1 < d0) {
-        bad |= BAD_TOO_LARGE;
-        d1 = d0;
-    }
-    uint32_t L = live ? d1 - d0 : 0;
-    uint64_t h0 = 0;
-    uint32_t H = 0;
-    if (!ALIAS) {
-        if (p.host_off) {
-            uint32_t a = p.host_off[r], b = p.host_off[r + 1];
-            if (b < a) {
-                bad |= BAD_TOO_LARGE;
-                b = a;
-            }
-            h0 = a;
-            H = b - a;
-        } else {
-            h0 = r * p.host_stride;
-            H = p.host_stride;
-        }
-        if (!live)
-            H = 0;
-    }
-
-    /* tile extents in the packed input streams */
-    const uint64_t D0 = p.domain_off[r0], D1 = p.domain_off[r0 + nrec];
-    uint64_t HB0 = 0, HB1 = 0;
-    if (!ALIAS) {
-        HB0 = p.host_off ? (uint64_t)p.host_off[r0] : r0 * p.host_stride;
-        HB1 = p.host_off ? (uint64_t)p.host_off[r0 + nrec] : (r0 + nrec) * p.host_stride;
-    }
-    const uint64_t dom_a0 = D0 & ~15ull, host_a0 = HB0 & ~15ull;
-    const bool fits = !p.force_generic && D1 >= D0 && HB1 >= HB0 && (D1 - dom_a0) <= p.dom_cap &&
-        (ALIAS || (HB1 - host_a0) <= p.host_cap) &&
-        ((D1 - D0) + (HB1 - HB0) + 2ull * nrec + 16) <= p.out_cap;
-
-    /* offsets that are not monotonic or point outside the buffers: refuse the tile (memory safety) */
-    {
-        bool rec_broken = live && (p.domain_off[r + 1] < d0 || d0 < D0 || d1 > D1);
-        if (!ALIAS && p.host_off && live)
-            rec_broken = rec_broken || p.host_off[r + 1] < p.host_off[r] || h0 < HB0 || h0 + H > HB1;
-        const bool tile_broken = D1 < D0 || D1 > p.dom_limit || (!ALIAS && (HB1 < HB0 || HB1 > p.host_limit));
-        if (__syncthreads_or(rec_broken || tile_broken)) {
-            if (live && (rec_broken || tile_broken))
-                report_bad(p.status, BAD_TOO_LARGE, r);
-            return;
-        }
-    }
-
-    /* where the tile and the record go.  Closed form: slot = L + 2 + H bytes (alias: L + 1). */
-    unsigned long long tile_base;
-    uint32_t tile_total = 0, local = 0, slot = 0;
-    if (!exact) {
-        const unsigned long long cf0 = (unsigned long long)D0 + (ALIAS ? r0 : HB0 + 2ull * r0);
-        const unsigned long long cf1 = (unsigned long long)D1 + (ALIAS ? r0 + nrec : HB1 + 2ull * (r0 + nrec));
-        tile_base = cf0;
-        tile_total = (uint32_t)(cf1 - cf0);
-        local = (uint32_t)(((unsigned long long)d0 + (ALIAS ? r : h0 + 2ull * r)) - cf0);
-        slot = ALIAS ? L + 1u : L + 2u + H;
-    } else {
-        tile_base = p.tile_base[tile];
-        tile_total = (uint32_t)(p.tile_base[tile + 1] - tile_base);
-    }
-
-    uint32_t len;
-    if (fits) {
-        stage_in(s_dom, p.domain_bytes, D0, D1, p.dom_limit);
-        if (!ALIAS)
-            stage_in(s_host, p.host_bytes, HB0, HB1, p.host_limit);
-        __syncthreads();
-        /* cooperative pre-pass: lower-case, dot bitmap, fence (vectorised, no divergence) */
-        uint32_t suspicious = prepass_domain(reinterpret_cast<uint32_t *>(s_dom), reinterpret_cast<uint16_t *>(s_bits),
-            (uint32_t)((D1 - dom_a0 + 15) >> 4), t, TILE);
-        if (!ALIAS)
-            suspicious |= prepass_host(reinterpret_cast<const uint32_t *>(s_host), (uint32_t)((HB1 - host_a0 + 15) >> 4),
-                t, TILE);
-        suspicious = __syncthreads_or(suspicious != 0);
-        const PaddedWords dsrc{reinterpret_cast<const uint32_t *>(s_dom)};
-        const PaddedWords hsrc{reinterpret_cast<const uint32_t *>(s_host)};
-        const uint32_t doff = (uint32_t)(d0 - dom_a0);
-        const uint32_t hoff = (uint32_t)(h0 - host_a0);
-        const DomainInfo di = domain_info(reinterpret_cast<const uint32_t *>(s_bits), doff, L);
-        if (suspicious) {
-            /* something in or next to this tile is outside the fence: find out exactly which records */
-            bad |= scan_domain(dsrc, doff, L).bad;
-            if (!ALIAS && live)
-                bad |= check_host(hsrc, hoff, H);
-        } else if (!ALIAS && live && H <= 2) {
-            bad |= check_host(hsrc, hoff, H);                   /* "", "." and ".." have no bad byte */
-        }
-        len = live ? path_length2(di, L, H, ALIAS) : 0;
-        if (exact) {
-            uint32_t tot;
-            local = block_scan<uint32_t>(warp_sum, len, &tot);
-        } else if (live && len != slot) {
-            atomicOr(&p.status->needs_exact, 1u);               /* empty labels: redo with exact offsets */
-        }
-        if (live)
-            p.out_off[r] = tile_base + local;
-        const bool room = tile_base + tile_total <= p.out_capacity;
-        if (room) {
-            const uint32_t shift = (uint32_t)(tile_base & 15ull);
-            WordSink sink;
-            sink.init(reinterpret_cast<uint32_t *>(s_out), local + shift);
-            if (live)
-                emit_path2<ALIAS>(dsrc, doff, L, di, hsrc, hoff, H, sink);
-            __syncthreads();
-            if (live)
-                sink.tail();                                    /* phase B: shared boundary words */
-            __syncthreads();
-            flush_out(p.out_bytes, s_out, tile_base, tile_total);
-        } else if (t == 0) {
-            atomicOr(&p.status->overflow, 1u);
-        }
-    } else {
-        /* generic path: compose straight from / to global memory */
-        const GuardedWords dsrc{reinterpret_cast<const uint32_t *>(p.domain_bytes)};
-        const GuardedWords hsrc{reinterpret_cast<const uint32_t *>(p.host_bytes)};
-        DomainStats st = scan_domain(dsrc, d0, L);
-        bad |= st.bad;
-        if (!ALIAS && live)
-            bad |= check_host(hsrc, (uint32_t)h0, H);
-        len = live ? path_length(st, L, H, ALIAS) : 0;
-        if (exact) {
-            uint32_t tot;
-            local = block_scan<uint32_t>(warp_sum, len, &tot);
-        } else if (live && len != slot) {
-            atomicOr(&p.status->needs_exact, 1u);
-        }
-        if (live)
-            p.out_off[r] = tile_base + local;
-        const bool room = tile_base + tile_total <= p.out_capacity;
-        if (room) {
-            if (live) {
-                ByteSink sink;
-                sink.init(p.out_bytes + tile_base + local);
-                emit_path<ALIAS>(dsrc, d0, L, hsrc, (uint32_t)h0, H, sink);
-            }
-        } else if (t == 0) {
-            atomicOr(&p.status->overflow, 1u);
-        }
-    }
-    if (live)
-        report_bad(p.status, bad, r);
-    if (r0 + nrec == p.n && t == 0) {
-        p.out_off[p.n] = tile_base + tile_total;
-        p.status->path_total = tile_base + tile_total;
-    }
-}
-
-/* ============================================================= payloads == */
+/* ======================================================= payload metadata == */
 
 struct JsonParams {
     uint64_t n;
@@ -435,9 +230,8 @@ struct JsonParams {
     uint8_t *out_bytes;
     unsigned long long *out_off;
     uint64_t out_capacity;
-    uint32_t *tile_total;               /* [ntiles], written by the length kernel */
-    unsigned long long *tile_base;      /* [ntiles+1], written by the length kernel's last CTA */
-    uint32_t *counter;
+    uint32_t *tile_total;               /* [ntiles] payload bytes per tile, accumulated by the producer kernel */
+    unsigned long long *super_total;    /* [ntiles / SUPER + 1] */
     DevStatus *status;
     uint64_t addr_limit, ports_limit;   /* bytes behind addr_bytes / elements behind ports (trusted) */
     uint32_t out_cap;                   /* shared-memory budget of the output image */
@@ -497,27 +291,309 @@ __device__ __forceinline__ uint32_t json_meta_len(const JsonParams &p, const Jso
     return json_length(tf.f1_len, tf.f2_len, m.al, m.has_ttl, m.ttl, m.has_ports, m.k, port_digits);
 }
 
-/* Payload lengths from the metadata only (no string bytes) -> per-tile totals -> per-tile bases. */
-__global__ void __launch_bounds__(TILE) regk_json_len_kernel(const JsonParams p)
+/* ================================================================ paths == */
+
+struct PathParams {
+    uint64_t n;
+    const uint8_t *domain_bytes;
+    const uint32_t *domain_off;
+    const uint8_t *host_bytes;
+    const uint32_t *host_off;           /* NULL: fixed stride */
+    uint32_t host_stride;
+    uint8_t *out_bytes;
+    unsigned long long *out_off;        /* [n+1] */
+    uint64_t out_capacity;
+    uint32_t exact;                     /* 0: closed-form offsets; 1: bases from tile_total / super_total */
+    uint32_t *tile_total;               /* [ntiles]   exact path bytes per tile (regk_path_len_kernel) */
+    unsigned long long *super_total;    /* [ntiles / SUPER + 1] */
+    DevStatus *status;
+    uint64_t dom_limit, host_limit;     /* bytes behind domain_bytes / host_bytes (trusted, from the caller) */
+    uint32_t dom_cap, host_cap, out_cap;        /* shared-memory budgets in bytes */
+    uint32_t force_generic;
+};
+
+/* closed-form offset of record r's path when no label is empty: path_len = L + 2 + H (alias: L + 1) */
+template <bool ALIAS>
+__device__ __forceinline__ unsigned long long path_cf(const PathParams &p, uint64_t r)
 {
-    __shared__ uint32_t warp_sum[WARPS];
+    unsigned long long v = (unsigned long long)p.domain_off[r];
+    if (ALIAS)
+        return v + r;
+    return v + 2ull * r + (p.host_off ? (unsigned long long)p.host_off[r] : r * (unsigned long long)p.host_stride);
+}
+
+/*
+ * Exact path lengths -> per-tile totals -> per-tile bases.  Only launched when the compose
+ * kernel reported `needs_exact` (some domain has empty labels, which path.join drops).
+ */
+template <bool ALIAS>
+__global__ void __launch_bounds__(TILE) regk_path_len_kernel(const PathParams p)
+{
     const uint32_t tile = blockIdx.x, t = threadIdx.x;
     const uint64_t r0 = (uint64_t)tile * TILE;
     const uint32_t nrec = (uint32_t)min((uint64_t)TILE, p.n - r0);
     uint32_t len = 0;
     if (t < nrec) {
-        const JsonMeta m = json_meta(p, r0 + t);
-        const TypeFrag tf = reinterpret_cast<const TypeFrag *>(p.frag_blob)[m.tid];
-        len = json_meta_len(p, m, tf);
+        const uint64_t r = r0 + t;
+        const uint32_t d0 = p.domain_off[r], d1 = p.domain_off[r + 1];
+        const uint32_t L = (d1 >= d0 && d1 <= p.dom_limit) ? d1 - d0 : 0;   /* corrupt offsets: flagged by the compose kernel */
+        uint32_t H = 0;
+        if (!ALIAS) {
+            if (p.host_off) {
+                const uint32_t a = p.host_off[r], b = p.host_off[r + 1];
+                H = b >= a ? b - a : 0;
+            } else {
+                H = p.host_stride;
+            }
+        }
+        const GuardedWords dsrc{reinterpret_cast<const uint32_t *>(p.domain_bytes)};
+        len = path_length(scan_domain(dsrc, d0, L), L, H, ALIAS);
     }
-    uint32_t total;
-    block_scan<uint32_t>(warp_sum, len, &total);
-    if (t == 0)
-        p.tile_total[tile] = total;
-    finalize_bases(p.tile_total, p.tile_base, gridDim.x, p.counter);
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        len += __shfl_xor_sync(0xFFFFFFFFu, len, d);
+    if ((t & 31u) == 0)
+        add_tile_total(p.tile_total, p.super_total, tile, len);
 }
 
-__global__ void __launch_bounds__(TILE, 3) regk_json_kernel(const JsonParams p)
+/* payload lengths of this tile -> tile_total / super_total (consumed by regk_json_kernel) */
+__device__ __forceinline__ void payload_length_side_job(const JsonParams &jp, const JsonMeta &jm, const TypeFrag &jtf,
+    bool live, uint32_t tile)
+{
+    uint32_t jl = live ? json_meta_len(jp, jm, jtf) : 0;
+    #pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+        jl += __shfl_xor_sync(0xFFFFFFFFu, jl, d);
+    if ((threadIdx.x & 31u) == 0)
+        add_tile_total(jp.tile_total, jp.super_total, tile, jl);
+}
+
+/*
+ * `jp.n != 0` turns on a side job: this kernel also computes the PAYLOAD length of each of its records
+ * (metadata only; the loads overlap the staging of the path inputs) and adds the per-warp sums into
+ * jp.tile_total / jp.super_total, from which every CTA of regk_json_kernel derives its base — no separate
+ * pass over the payload metadata and no scan launch.
+ */
+template <bool ALIAS>
+__global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const PathParams p, const JsonParams jp)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint32_t warp_sum[WARPS];
+    uint8_t *s_dom = smem;                                      /* staged domain bytes, lower-cased in place */
+    uint8_t *s_bits = s_dom + p.dom_cap + 32;                   /* 1 bit per staged domain byte: is '.' */
+    uint8_t *s_host = s_bits + p.dom_cap / 8 + 16;
+    uint8_t *s_out = s_host + (ALIAS ? 0 : p.host_cap + 32);
+
+    const uint32_t tile = blockIdx.x;
+    const uint64_t r0 = (uint64_t)tile * TILE;
+    const uint32_t nrec = (uint32_t)min((uint64_t)TILE, p.n - r0);
+    const uint32_t t = threadIdx.x;
+    const bool live = t < nrec;
+    const uint64_t r = r0 + (live ? t : 0);
+    const bool exact = p.exact != 0;
+
+    /* per-record extents */
+    uint32_t d0 = p.domain_off[r], d1 = p.domain_off[r + 1];
+    uint32_t bad = 0;
+    if (d1 < d0) {
+        bad |= BAD_TOO_LARGE;
+        d1 = d0;
+    }
+    uint32_t L = live ? d1 - d0 : 0;
+    uint64_t h0 = 0;
+    uint32_t H = 0;
+    if (!ALIAS) {
+        if (p.host_off) {
+            uint32_t a = p.host_off[r], b = p.host_off[r + 1];
+            if (b < a) {
+                bad |= BAD_TOO_LARGE;
+                b = a;
+            }
+            h0 = a;
+            H = b - a;
+        } else {
+            h0 = r * p.host_stride;
+            H = p.host_stride;
+        }
+        if (!live)
+            H = 0;
+    }
+
+    /* tile extents in the packed input streams */
+    const uint64_t D0 = p.domain_off[r0], D1 = p.domain_off[r0 + nrec];
+    uint64_t HB0 = 0, HB1 = 0;
+    if (!ALIAS) {
+        HB0 = p.host_off ? (uint64_t)p.host_off[r0] : r0 * p.host_stride;
+        HB1 = p.host_off ? (uint64_t)p.host_off[r0 + nrec] : (r0 + nrec) * p.host_stride;
+    }
+    const uint64_t dom_a0 = D0 & ~15ull, host_a0 = HB0 & ~15ull;
+    const bool fits = !p.force_generic && D1 >= D0 && HB1 >= HB0 && (D1 - dom_a0) <= p.dom_cap &&
+        (ALIAS || (HB1 - host_a0) <= p.host_cap) &&
+        ((D1 - D0) + (HB1 - HB0) + 2ull * nrec + 16) <= p.out_cap;
+
+    /* side job, part 1: issue the payload-metadata loads now so they overlap the staging below */
+    const bool side = jp.n != 0;
+    JsonMeta jm;
+    TypeFrag jtf;
+    if (side) {
+        jm = json_meta(jp, r);
+        jtf = reinterpret_cast<const TypeFrag *>(jp.frag_blob)[jm.tid];
+    }
+
+    /* offsets that are not monotonic or point outside the buffers: refuse the tile (memory safety) */
+    {
+        bool rec_broken = live && (p.domain_off[r + 1] < d0 || d0 < D0 || d1 > D1);
+        if (!ALIAS && p.host_off && live)
+            rec_broken = rec_broken || p.host_off[r + 1] < p.host_off[r] || h0 < HB0 || h0 + H > HB1;
+        const bool tile_broken = D1 < D0 || D1 > p.dom_limit || (!ALIAS && (HB1 < HB0 || HB1 > p.host_limit));
+        if (__syncthreads_or(rec_broken || tile_broken)) {
+            if (live && (rec_broken || tile_broken))
+                report_bad(p.status, BAD_TOO_LARGE, r);
+            if (side)
+                payload_length_side_job(jp, jm, jtf, live, tile);
+            return;
+        }
+    }
+
+    /* where the tile and the record go.  Closed form: slot = L + 2 + H bytes (alias: L + 1). */
+    unsigned long long tile_base;
+    uint32_t tile_total = 0, local = 0, slot = 0;
+    if (!exact) {
+        const unsigned long long cf0 = (unsigned long long)D0 + (ALIAS ? r0 : HB0 + 2ull * r0);
+        const unsigned long long cf1 = (unsigned long long)D1 + (ALIAS ? r0 + nrec : HB1 + 2ull * (r0 + nrec));
+        tile_base = cf0;
+        tile_total = (uint32_t)(cf1 - cf0);
+        local = (uint32_t)(((unsigned long long)d0 + (ALIAS ? r : h0 + 2ull * r)) - cf0);
+        slot = ALIAS ? L + 1u : L + 2u + H;
+    } else {
+        __shared__ unsigned long long s_exact_base;
+        if (t < 32) {
+            const unsigned long long b = tile_base_from_totals(p.tile_total, p.super_total, tile);
+            if (t == 0)
+                s_exact_base = b;
+        }
+        __syncthreads();
+        tile_base = s_exact_base;
+        tile_total = p.tile_total[tile];
+    }
+
+    uint32_t len;
+    if (fits) {
+        stage_in(s_dom, p.domain_bytes, D0, D1, p.dom_limit);
+        if (!ALIAS)
+            stage_in(s_host, p.host_bytes, HB0, HB1, p.host_limit);
+        __syncthreads();
+        /* cooperative pre-pass: lower-case, dot bitmap, fence (vectorised, no divergence) */
+        uint32_t suspicious = prepass_domain(reinterpret_cast<uint32_t *>(s_dom), reinterpret_cast<uint16_t *>(s_bits),
+            (uint32_t)((D1 - dom_a0 + 15) >> 4), t, TILE);
+        if (!ALIAS)
+            suspicious |= prepass_host(reinterpret_cast<const uint32_t *>(s_host), (uint32_t)((HB1 - host_a0 + 15) >> 4),
+                t, TILE);
+        suspicious = __syncthreads_or(suspicious != 0);
+        const PaddedWords dsrc{reinterpret_cast<const uint32_t *>(s_dom)};
+        const PaddedWords hsrc{reinterpret_cast<const uint32_t *>(s_host)};
+        const uint32_t doff = (uint32_t)(d0 - dom_a0);
+        const uint32_t hoff = (uint32_t)(h0 - host_a0);
+        const DomainInfo di = domain_info(reinterpret_cast<const uint32_t *>(s_bits), doff, L);
+        if (suspicious) {
+            /* something in or next to this tile is outside the fence: find out exactly which records */
+            bad |= scan_domain(dsrc, doff, L).bad;
+            if (!ALIAS && live)
+                bad |= check_host(hsrc, hoff, H);
+        } else if (!ALIAS && live && H <= 2) {
+            bad |= check_host(hsrc, hoff, H);                   /* "", "." and ".." have no bad byte */
+        }
+        len = live ? path_length2(di, L, H, ALIAS) : 0;
+        if (exact) {
+            uint32_t tot;
+            local = block_scan<uint32_t>(warp_sum, len, &tot);
+        } else if (live && len != slot) {
+            atomicOr(&p.status->needs_exact, 1u);               /* empty labels: redo with exact offsets */
+        }
+        if (live)
+            p.out_off[r] = tile_base + local;
+        const bool room = tile_base + tile_total <= p.out_capacity;
+        if (room) {
+            const uint32_t shift = (uint32_t)(tile_base & 15ull);
+            WordSink sink;
+            sink.init(reinterpret_cast<uint32_t *>(s_out), local + shift);
+            if (live)
+                emit_path2<ALIAS>(dsrc, doff, L, di, hsrc, hoff, H, sink);
+            __syncthreads();
+            if (live)
+                sink.tail();                                    /* phase B: shared boundary words */
+            fence_proxy_async();
+            __syncthreads();
+            flush_out(p.out_bytes, s_out, tile_base, tile_total);
+        } else if (t == 0) {
+            atomicOr(&p.status->overflow, 1u);
+        }
+    } else {
+        /* generic path: compose straight from / to global memory */
+        const GuardedWords dsrc{reinterpret_cast<const uint32_t *>(p.domain_bytes)};
+        const GuardedWords hsrc{reinterpret_cast<const uint32_t *>(p.host_bytes)};
+        DomainStats st = scan_domain(dsrc, d0, L);
+        bad |= st.bad;
+        if (!ALIAS && live)
+            bad |= check_host(hsrc, (uint32_t)h0, H);
+        len = live ? path_length(st, L, H, ALIAS) : 0;
+        if (exact) {
+            uint32_t tot;
+            local = block_scan<uint32_t>(warp_sum, len, &tot);
+        } else if (live && len != slot) {
+            atomicOr(&p.status->needs_exact, 1u);
+        }
+        if (live)
+            p.out_off[r] = tile_base + local;
+        const bool room = tile_base + tile_total <= p.out_capacity;
+        if (room) {
+            if (live) {
+                ByteSink sink;
+                sink.init(p.out_bytes + tile_base + local);
+                emit_path<ALIAS>(dsrc, d0, L, hsrc, (uint32_t)h0, H, sink);
+            }
+        } else if (t == 0) {
+            atomicOr(&p.status->overflow, 1u);
+        }
+    }
+    if (live)
+        report_bad(p.status, bad, r);
+    if (r0 + nrec == p.n && t == 0) {
+        p.out_off[p.n] = tile_base + tile_total;
+        p.status->path_total = tile_base + tile_total;
+    }
+    if (side)
+        payload_length_side_job(jp, jm, jtf, live, tile);      /* part 2 */
+}
+
+/* ============================================================= payloads == */
+
+/*
+ * Payload lengths from the metadata only (no string bytes) -> per-tile totals -> per-tile bases.
+ * Only used when the path half is skipped (REGK_NO_PATH).  Persistent grid: each CTA walks tiles
+ * blockIdx.x, +gridDim.x, ...; a warp sums its 32 records with shuffles and adds the sum to the tile's
+ * totals (zeroed by the host) with atomics.
+ */
+__global__ void __launch_bounds__(TILE) regk_json_len_kernel(const JsonParams p, uint32_t ntiles)
+{
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t r = (uint64_t)tile * TILE + t;
+        uint32_t len = 0;
+        if (r < p.n) {
+            const JsonMeta m = json_meta(p, r);
+            const TypeFrag tf = reinterpret_cast<const TypeFrag *>(p.frag_blob)[m.tid];
+            len = json_meta_len(p, m, tf);
+        }
+        #pragma unroll
+        for (int d = 16; d > 0; d >>= 1)
+            len += __shfl_xor_sync(0xFFFFFFFFu, len, d);
+        if (lane == 0)
+            add_tile_total(p.tile_total, p.super_total, tile, len);
+    }
+}
+
+__global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const JsonParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t warp_sum[WARPS];
@@ -538,8 +614,13 @@ __global__ void __launch_bounds__(TILE, 3) regk_json_kernel(const JsonParams p)
     const JsonMeta m = json_meta(p, r);
     uint32_t bad = m.bad;
     const uint32_t a0 = m.a0, al = m.al, k = m.k;
-    const unsigned long long tile_base = p.tile_base[tile];
-    const uint32_t tile_total = (uint32_t)(p.tile_base[tile + 1] - tile_base);
+    __shared__ unsigned long long s_base;
+    if (t < 32) {                                               /* warp 0: this tile's base from the two-level totals */
+        const unsigned long long b = tile_base_from_totals(p.tile_total, p.super_total, tile);
+        if (t == 0)
+            s_base = b;
+    }
+    const uint32_t tile_total = p.tile_total[tile];
 
     /* first 16 address bytes -> registers, fenced */
     const GuardedWords asrc{reinterpret_cast<const uint32_t *>(p.addr_bytes)};
@@ -568,7 +649,8 @@ __global__ void __launch_bounds__(TILE, 3) regk_json_kernel(const JsonParams p)
                 bad |= BAD_ADDR_BYTE;
         }
     }
-    __syncthreads();                                            /* fragment table is visible */
+    __syncthreads();                                            /* fragment table and s_base are visible */
+    const unsigned long long tile_base = s_base;
     const TypeFrag tf = reinterpret_cast<const TypeFrag *>(s_blob)[m.tid];
     const uint32_t len = live ? json_meta_len(p, m, tf) : 0;
     uint32_t tot;
@@ -593,6 +675,7 @@ __global__ void __launch_bounds__(TILE, 3) regk_json_kernel(const JsonParams p)
         __syncthreads();
         if (live)
             sink.tail();                                        /* phase B: shared boundary words */
+        fence_proxy_async();
         __syncthreads();
         flush_out(p.out_bytes, s_out, tile_base, tile_total);
     } else if (live) {

@@ -5,8 +5,10 @@
  * For every record type T (registration.type, lib/register.js:142) two byte
  * strings are precomputed, JSON-escaped once (ECMA-262 QuoteJSONString):
  *     f1 = {"type":"T","address":"          f2 = ,"T":{"address":"
- * Blob layout: TypeFrag[ntypes] (padded to 16 bytes) followed by the fragments,
- * each starting on a 4-byte boundary; total size padded to 16 bytes.
+ * Blob layout: TypeFrag[ntypes] (padded to 16 bytes) followed by the fragments.  Every
+ * fragment is stored four times, pre-shifted by 0..3 zero bytes and zero padded to
+ * frag_stride_words(len) words, so the kernel can append it at any byte phase of the
+ * output with plain word copies; total size padded to 16 bytes.
  */
 #ifndef REGK_TYPES_HPP
 #define REGK_TYPES_HPP
@@ -92,9 +94,15 @@ inline int build_type_blob(const std::vector<std::string> &types, std::vector<ui
                 bytes.push_back(0);
             off = (uint16_t)(table + bytes.size());
             len = (uint16_t)f.size();
-            bytes.insert(bytes.end(), f.begin(), f.end());
+            const size_t stride = frag_stride_words((uint32_t)f.size()) * 4;
+            for (size_t shift = 0; shift < 4; shift++) {
+                const size_t start = bytes.size();
+                bytes.insert(bytes.end(), shift, 0);
+                bytes.insert(bytes.end(), f.begin(), f.end());
+                bytes.resize(start + stride, 0);
+            }
         };
-        if (table + bytes.size() + f1.size() + f2.size() + 8 > TYPE_BLOB_MAX) {
+        if (table + bytes.size() + 4 * (f1.size() + f2.size() + 16) > TYPE_BLOB_MAX) {
             *err = "fragment table exceeds the shared-memory budget of 16384 bytes";
             return 2;
         }

@@ -7,6 +7,8 @@ from registrar_b200.batch import RecordBatch
 
 def main():
     ctx = _native.Context(0)
+    if os.environ.get('REGK_DOMCAP'):
+        ctx.set_option('dom_cap', int(os.environ['REGK_DOMCAP']))
     out = []
     for cfg, n in [("config2", 1_000_000), ("config3", 2_000_000), ("config5", 2_000_000)]:
         b = synth.generate(cfg, n=n)
