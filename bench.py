@@ -5,7 +5,8 @@
     python bench.py --impl reference --gpus 1 ...             # CPU arm: the oracle port on the host cores
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one pass of the hot path (path kernel + payload kernel) over one batch of synthetic records.
+A step = one pass of the hot path over one batch of synthetic records: regk_path_kernel (paths + offsets, and
+the payload lengths as a side job) followed by regk_json_kernel (payload bytes + offsets) — 2 launches.
 Workload at every N: BASELINE.json configs[1] per GPU — 1M records, 3-label domains + instance UUID
 (weak scaling: rank r owns its own 1M-record shards of the synthetic stream; no data-path collective).
 
@@ -38,6 +39,9 @@ import numpy as np  # noqa: E402
 METRIC = "service-records/sec"
 UNIT = "records/s"
 NB = 4                      # distinct resident batches rotated through the timed loop
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+# workload (profiles/); None until a capture of the current kernels exists.
+NCU_TRAFFIC = {"path": 92214016, "json": 70110976}     # profiles/r1_ncu_v5_two_level_totals.txt (config2, 1M records)
 
 
 def load_peaks():
@@ -265,6 +269,8 @@ def run_b200(args):
                     "mean_launch_ms": round(ms, 5), "peak_source": peak_src}
 
         roofs = {"path": roof("regk_path_kernel<false>", pb, p_ms), "json": roof("regk_json_kernel", jb, j_ms)}
+        for k in roofs:
+            roofs[k]["traffic"] = NCU_TRAFFIC.get(k)
         dominant = "path" if p_ms >= j_ms else "json"
         both = (pb + jb) / ((p_ms + j_ms) * 1e-3) / 1e9 if p_ms + j_ms > 0 else 0.0
         line = {

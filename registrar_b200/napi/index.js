@@ -1,0 +1,145 @@
+/*
+ * index.js — drop-in for the registration half of registrar's lib/register.js on top of the N-API addon.
+ *
+ *   var register = require('registrar-b200').register;     // same (opts, cb) as lib/register.js:174
+ *
+ * Only the per-record compute changes hands: domainToPath (register.js:34-39), path.join with the hostname
+ * (:221-223) and the payload bytes (:141-159) come back from one GPU batch of 1 + aliases records; the
+ * ZooKeeper choreography (unlink, 1 s wait, mkdirp, create, put) is the reference's, driven through the same
+ * duck-typed opts.zk.  zk.create() receives a Buffer (already-serialised payload) instead of an object.
+ *
+ * Not runnable in the development image (no Node.js); the Python mirror registrar_b200/registration.py is
+ * the tested implementation of exactly this logic.
+ */
+var os = require('os');
+var path = require('path');
+var assert = require('assert-plus');
+var once = require('once');
+var vasync = require('vasync');
+var regk = require('./build/Release/regk_napi.node');
+
+var TTL_ABSENT = -2147483648;
+var FLAG_NODE_ALIAS = 1 << 2, FLAG_NO_JSON = 1 << 3;
+
+regk.init(0);
+
+function packStrings(strs) {
+    var off = Buffer.alloc(4 * (strs.length + 1)), bufs = strs.map(function (s) { return (Buffer.from(s, 'utf8')); });
+    var tot = 0;
+    bufs.forEach(function (b, i) { tot += b.length; off.writeUInt32LE(tot, 4 * (i + 1)); });
+    return ({ bytes: Buffer.concat(bufs), off: off });
+}
+
+function toBatch(records, types, flags) {
+    var d = packStrings(records.map(function (r) { return (r.domain); }));
+    var h = packStrings(records.map(function (r) { return (r.hostname || ''); }));
+    var a = packStrings(records.map(function (r) { return (r.address); }));
+    var n = records.length;
+    var typeId = Buffer.alloc(n), ttl = Buffer.alloc(4 * n), portsOff = Buffer.alloc(4 * (n + 1)),
+        present = Buffer.alloc(n), flat = [];
+    records.forEach(function (r, i) {
+        typeId[i] = types.indexOf(r.type);
+        ttl.writeInt32LE(r.ttl === undefined ? TTL_ABSENT : r.ttl, 4 * i);
+        if (r.ports) { present[i] = 1; flat = flat.concat(r.ports); }
+        portsOff.writeUInt32LE(flat.length, 4 * (i + 1));
+    });
+    var ports = Buffer.alloc(4 * Math.max(flat.length, 1));
+    flat.forEach(function (p, i) { ports.writeUInt32LE(p, 4 * i); });
+    return ({ n: n, flags: flags, hostStride: 0, domainBytes: d.bytes, domainOff: d.off, hostBytes: h.bytes,
+        hostOff: h.off, typeId: typeId, addrBytes: a.bytes, addrOff: a.off, ttl: ttl, portsOff: portsOff,
+        ports: ports, portsPresent: present });
+}
+
+function slices(bytes, off, n) {
+    var out = [], i;
+    for (i = 0; i < n; i++)
+        out.push(bytes.slice(Number(off.readBigUInt64LE(8 * i)), Number(off.readBigUInt64LE(8 * (i + 1)))));
+    return (out);
+}
+
+function registerBatch(records, cb) {
+    var types = [];
+    records.forEach(function (r) { if (types.indexOf(r.type) === -1) types.push(r.type); });
+    regk.setTypes(types);
+    regk.registerBatch(toBatch(records, types, 0), function (err, res) {
+        if (err) { cb(err); return; }
+        cb(null, { paths: slices(res.pathBytes, res.pathOff, records.length),
+            payloads: slices(res.jsonBytes, res.jsonOff, records.length), kernelMs: res.kernelMs });
+    });
+}
+
+function register(opts, cb) {
+    /* argument contract: lib/register.js:175-201, verbatim semantics */
+    assert.object(opts, 'options');
+    assert.object(opts.log, 'options.log');
+    assert.optionalString(opts.adminIp, 'options.adminIp');
+    assert.optionalObject(opts.aliases, 'options.aliases');
+    assert.string(opts.domain, 'options.domain');
+    assert.object(opts.registration, 'options.registration');
+    assert.string(opts.registration.type, 'options.registration.type');
+    assert.optionalNumber(opts.registration.ttl, 'options.registration.ttl');
+    assert.optionalArrayOfNumber(opts.registration.ports, 'options.registration.ports');
+    assert.optionalObject(opts.registration.service, 'options.registration.service');
+    if (opts.registration.service) {
+        var s2 = opts.registration.service.service;
+        assert.ok(opts.registration.service.type === 'service');
+        assert.object(s2, 'options.registration.service.service');
+        assert.string(s2.srvce, 'options.registration.service.service.srvce');
+        assert.string(s2.proto, 'options.registration.service.service.proto');
+        assert.optionalNumber(s2.ttl, 'options.registration.service.service.ttl');
+        s2.ttl = s2.ttl !== undefined ? s2.ttl : 60;
+        assert.number(s2.port, 'options.registration.service.service.port');
+    }
+    assert.object(opts.zk, 'options.zk');
+    assert.func(cb, 'callback');
+    cb = once(cb);
+
+    var reg = opts.registration, zk = opts.zk, aliases = opts.aliases || [];
+    var ports = reg.ports ? reg.ports : (reg.service ? [ reg.service.service.port ] : undefined);
+    var address = opts.adminIp ? opts.adminIp : firstAddress();
+    var types = [ reg.type ];
+    regk.setTypes(types);
+    var host = [ { domain: opts.domain, hostname: os.hostname(), type: reg.type, address: address, ttl: reg.ttl, ports: ports } ];
+    var names = [ opts.domain ].concat(aliases).map(function (d) { return ({ domain: d, type: reg.type, address: address }); });
+    regk.registerBatch(toBatch(host, types, 0), function (err, h) {
+        if (err) { cb(err); return; }
+        regk.registerBatch(toBatch(names, types, FLAG_NODE_ALIAS | FLAG_NO_JSON), function (err2, a) {
+            if (err2) { cb(err2); return; }
+            var aliasPaths = slices(a.pathBytes, a.pathOff, names.length).map(String);
+            var cookie = { nodes: [ String(slices(h.pathBytes, h.pathOff, 1)[0]) ].concat(aliasPaths.slice(1)),
+                path: aliasPaths[0], payload: slices(h.jsonBytes, h.jsonOff, 1)[0] };
+            vasync.pipeline({ arg: cookie, funcs: [
+                function cleanup(c, next) {
+                    vasync.forEachParallel({ inputs: c.nodes, func: function (n, _cb) {
+                        zk.unlink(n, function (e) { _cb(e && e.name !== 'NO_NODE' ? e : undefined); });
+                    } }, next);
+                },
+                function wait(_, next) { setTimeout(once(next), 1000); },
+                function mkdirs(c, next) {
+                    vasync.forEachParallel({ inputs: c.nodes.map(function (n) { return (path.dirname(n)); }),
+                        func: zk.mkdirp.bind(zk) }, next);
+                },
+                function entries(c, next) {
+                    vasync.forEachParallel({ inputs: c.nodes, func: function (n, _cb) {
+                        zk.create(n, c.payload, { flags: [ 'ephemeral_plus' ], serialized: true }, once(_cb));
+                    } }, next);
+                },
+                function service(c, next) {
+                    if (!reg.service) { next(); return; }
+                    zk.put(c.path, { type: 'service', service: reg.service }, function (e) {
+                        if (!e && c.nodes.indexOf(c.path) === -1) c.nodes.push(c.path);
+                        next(e);
+                    });
+                }
+            ] }, function (e) { if (e) cb(e); else cb(null, cookie.nodes); });
+        });
+    });
+}
+
+function firstAddress() {
+    var ifaces = os.networkInterfaces();
+    var k = Object.keys(ifaces).filter(function (x) { return (!ifaces[x][0].internal); })[0];
+    return (ifaces[k][0].address);
+}
+
+module.exports = { register: register, registerBatch: registerBatch };
