@@ -225,6 +225,8 @@ def run_b200(args):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     ctx.set_option("async", 0)
+    if os.environ.get("REGK_CHUNK"):
+        ctx.set_option("chunk_records", int(os.environ["REGK_CHUNK"]))
 
     # ---- end-to-end arm: host buffers through the public call ----
     pinned = [pinned_copy(ctx, hb) for hb in host_batches[:2]]

@@ -57,7 +57,9 @@ struct regk_ctx {
     DevBuf in[11];
     /* outputs */
     DevBuf path_bytes, path_off, json_bytes, json_off;
-    HostBuf h_path_bytes, h_path_off, h_json_bytes, h_json_off;
+    HostBuf h_path_bytes, h_path_off, h_json_bytes, h_json_off, h_running;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;          /* host pipelining (run_pipelined) */
+    std::vector<cudaEvent_t> pipe_events;
     /* workspace: DevStatus | tickets | tile status (stream-ordered reuse) */
     DevBuf work;
 
@@ -160,6 +162,215 @@ size_t align16(size_t v)
 
 }  // namespace
 
+/*
+ * Host buffers in, host buffers out, large batch: the PCIe copies dominate (config 2: 91 MB in, 171 MB out
+ * per million records against ~0.12 ms of kernels), so the batch is cut into chunks of `chunk` records and
+ * three streams overlap  H2D(chunk c+1) | kernels(chunk c) | D2H(chunk c-1).  Inputs land at their final
+ * positions in whole-batch device arrays, so offsets stay absolute; a chunk's kernels get pointer-shifted
+ * views, `off_bias` / `rec0` for the record numbering and a running payload base (device array) chained
+ * from chunk to chunk.  The host learns each chunk's payload byte range from a pinned copy of that running
+ * total once the chunk's kernels are done, then issues its D2H.
+ */
+struct HostPipe {
+    uint64_t chunk = 0, nchunks = 0, nsuper_chunk = 0;
+    unsigned long long *running = nullptr;      /* device, [nchunks + 1], zeroed */
+    uint64_t path_cap = 0, json_cap = 0;
+    const void *src[11] = {};
+    void *dev[11] = {};
+};
+
+static int run_pipelined(regk_ctx *ctx, const regk_batch *b, regk_result *res, const PathParams &pp0, size_t path_smem,
+    const JsonParams &jp0, size_t json_smem, const HostPipe &hp)
+{
+    const uint64_t n = b->n;
+    const bool alias = b->flags & REGK_NODE_ALIAS;
+    const bool do_path = !(b->flags & REGK_NO_PATH), do_json = !(b->flags & REGK_NO_JSON);
+    const uint32_t stride = b->host_stride;
+    cudaStream_t s = ctx->stream;
+    int rc;
+    if (!ctx->s_h2d) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    }
+    while (ctx->pipe_events.size() < 3 * hp.nchunks + 2) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
+    if ((rc = ensure_host(ctx, ctx->h_path_bytes, hp.path_cap)) || (rc = ensure_host(ctx, ctx->h_path_off, (n + 1) * 8)) ||
+        (rc = ensure_host(ctx, ctx->h_json_bytes, hp.json_cap)) || (rc = ensure_host(ctx, ctx->h_json_off, (n + 1) * 8)) ||
+        (rc = ensure_host(ctx, ctx->h_running, (hp.nchunks + 2) * 8)))
+        return rc;
+    unsigned long long *h_running = (unsigned long long *)ctx->h_running.p;
+    DevStatus *d_status = pp0.status ? pp0.status : jp0.status;
+    DevStatus *h_status = ctx->slots[0].h_status;
+
+    /* the workspace memset and the type table are ordered before everything on s */
+    cudaEvent_t e_ready = ctx->pipe_events[3 * hp.nchunks];
+    CK(cudaEventRecord(e_ready, s));
+    CK(cudaStreamWaitEvent(ctx->s_h2d, e_ready, 0));
+
+    const uint32_t *dom_off = (const uint32_t *)b->domain_off, *host_off = (const uint32_t *)b->host_off,
+                   *addr_off = (const uint32_t *)b->addr_off, *ports_off = (const uint32_t *)b->ports_off;
+    auto h2d = [&](int i, size_t byte_lo, size_t byte_hi) -> cudaError_t {
+        if (!hp.src[i] || !hp.dev[i] || byte_hi <= byte_lo)
+            return cudaSuccess;
+        return cudaMemcpyAsync((uint8_t *)hp.dev[i] + byte_lo, (const uint8_t *)hp.src[i] + byte_lo, byte_hi - byte_lo,
+            cudaMemcpyHostToDevice, ctx->s_h2d);
+    };
+    /* closed-form path offset of record r (no empty labels; verified by the kernel) */
+    auto path_cf = [&](uint64_t r) -> uint64_t {
+        if (alias)
+            return (uint64_t)dom_off[r] + r;
+        return (uint64_t)dom_off[r] + 2 * r + (host_off ? (uint64_t)host_off[r] : r * (uint64_t)stride);
+    };
+
+    uint32_t launches = 0;
+    for (uint64_t c = 0; c < hp.nchunks; c++) {
+        const uint64_t r0 = c * hp.chunk, r1 = std::min(n, r0 + hp.chunk), cn = r1 - r0;
+        const uint64_t t0 = r0 / TILE, ct = (cn + TILE - 1) / TILE;
+        cudaEvent_t e_in = ctx->pipe_events[3 * c], e_done = ctx->pipe_events[3 * c + 1];
+        /* ---- H2D of this chunk's slices ---- */
+        if (do_path) {
+            CK(h2d(1, r0 * 4, (r1 + 1) * 4));
+            CK(h2d(0, dom_off[r0], dom_off[r1]));
+            if (!alias) {
+                if (host_off) {
+                    CK(h2d(3, r0 * 4, (r1 + 1) * 4));
+                    CK(h2d(2, host_off[r0], host_off[r1]));
+                } else {
+                    CK(h2d(2, r0 * (size_t)stride, r1 * (size_t)stride));
+                }
+            }
+        }
+        if (do_json) {
+            CK(h2d(4, r0, r1));
+            CK(h2d(6, r0 * 4, (r1 + 1) * 4));
+            CK(h2d(5, addr_off[r0], addr_off[r1]));
+            CK(h2d(7, r0 * 4, r1 * 4));
+            if (ports_off) {
+                CK(h2d(8, r0 * 4, (r1 + 1) * 4));
+                CK(h2d(9, (size_t)ports_off[r0] * 4, (size_t)ports_off[r1] * 4));
+            }
+            CK(h2d(10, r0, r1));
+        }
+        CK(cudaEventRecord(e_in, ctx->s_h2d));
+        CK(cudaStreamWaitEvent(s, e_in, 0));
+        /* ---- kernels on pointer-shifted views ---- */
+        PathParams pp = pp0;
+        JsonParams jp = jp0;
+        if (do_json) {
+            jp.n = cn;
+            jp.rec0 = r0;
+            jp.type_id += r0;
+            jp.addr_off += r0;
+            if (jp.ttl)
+                jp.ttl += r0;
+            if (jp.ports_off)
+                jp.ports_off += r0;
+            if (jp.ports_present)
+                jp.ports_present += r0;
+            jp.out_off += r0;
+            jp.tile_total += t0;
+            jp.super_total += c * hp.nsuper_chunk;
+            jp.base_in = hp.running + c;
+            jp.base_out = hp.running + c + 1;
+        }
+        if (do_path) {
+            pp.n = cn;
+            pp.rec0 = r0;
+            pp.domain_off += r0;
+            if (pp.host_off) {
+                pp.host_off += r0;
+                pp.off_bias = alias ? r0 : 2 * r0;
+            } else if (!alias) {
+                pp.host_bytes += r0 * (size_t)stride;
+                pp.host_limit -= r0 * (uint64_t)stride;
+                pp.off_bias = r0 * (uint64_t)(stride + 2);
+            } else {
+                pp.off_bias = r0;
+            }
+            pp.out_off += r0;
+            pp.tile_total += t0;
+            pp.super_total += c * hp.nsuper_chunk;
+            const JsonParams side = do_json ? jp : JsonParams{};
+            if (alias)
+                regk_path_kernel<true><<<(unsigned)ct, TILE, path_smem, s>>>(pp, side);
+            else
+                regk_path_kernel<false><<<(unsigned)ct, TILE, path_smem, s>>>(pp, side);
+            CK(cudaGetLastError());
+            launches++;
+        }
+        if (do_json) {
+            if (!do_path) {
+                regk_json_len_kernel<<<(unsigned)std::min<uint64_t>(ct, (uint64_t)ctx->sm_count * 8), TILE, 0, s>>>(jp, (uint32_t)ct);
+                CK(cudaGetLastError());
+                launches++;
+            }
+            regk_json_kernel<<<(unsigned)ct, TILE, json_smem, s>>>(jp);
+            CK(cudaGetLastError());
+            launches++;
+            CK(cudaMemcpyAsync(h_running + c + 1, hp.running + c + 1, 8, cudaMemcpyDeviceToHost, s));
+        }
+        if (c + 1 == hp.nchunks)
+            CK(cudaMemcpyAsync(h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(e_done, s));
+    }
+    /* ---- D2H, chunk by chunk, as soon as each chunk's kernels are done ---- */
+    h_running[0] = 0;
+    for (uint64_t c = 0; c < hp.nchunks; c++) {
+        const uint64_t r0 = c * hp.chunk, r1 = std::min(n, r0 + hp.chunk);
+        cudaError_t e = cudaEventSynchronize(ctx->pipe_events[3 * c + 1]);
+        if (e != cudaSuccess)
+            return fail(ctx, REGK_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
+        const bool last = c + 1 == hp.nchunks;
+        if (do_path) {
+            const uint64_t lo = path_cf(r0), hi = std::min<uint64_t>(path_cf(r1), hp.path_cap);
+            if (hi > lo)
+                CK(cudaMemcpyAsync((uint8_t *)ctx->h_path_bytes.p + lo, (uint8_t *)ctx->path_bytes.p + lo, hi - lo,
+                    cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(cudaMemcpyAsync((uint64_t *)ctx->h_path_off.p + r0, (uint64_t *)ctx->path_off.p + r0, (r1 - r0 + (last ? 1 : 0)) * 8,
+                cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
+        if (do_json) {
+            const uint64_t lo = h_running[c], hi = std::min<uint64_t>(h_running[c + 1], hp.json_cap);
+            if (hi > lo)
+                CK(cudaMemcpyAsync((uint8_t *)ctx->h_json_bytes.p + lo, (uint8_t *)ctx->json_bytes.p + lo, hi - lo,
+                    cudaMemcpyDeviceToHost, ctx->s_d2h));
+            CK(cudaMemcpyAsync((uint64_t *)ctx->h_json_off.p + r0, (uint64_t *)ctx->json_off.p + r0, (r1 - r0 + (last ? 1 : 0)) * 8,
+                cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(ctx->s_d2h);
+    if (e != cudaSuccess)
+        return fail(ctx, REGK_ERR_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
+    const DevStatus st = *h_status;
+    memset(res, 0, sizeof *res);
+    res->n = n;
+    res->launches = launches;
+    res->bad_bits = st.bad_bits;
+    res->first_bad = st.bad_bits ? ~st.first_bad : 0;
+    if (st.overflow)
+        return fail(ctx, REGK_ERR_CUDA, "internal error: output capacity bound exceeded");
+    if (st.bad_bits)
+        return fail(ctx, REGK_ERR_OUT_OF_DOMAIN,
+            "record %llu is outside the supported input domain (REGK_BAD bits 0x%x); no output produced",
+            (unsigned long long)res->first_bad, st.bad_bits);
+    if (st.needs_exact)
+        return REGK_ERR_STATE + 100;            /* caller re-runs the batch through the exact-capable path */
+    res->path_total = st.path_total;
+    res->json_total = st.json_total;
+    res->path_bytes = (uint8_t *)ctx->h_path_bytes.p;
+    res->path_off = (uint64_t *)ctx->h_path_off.p;
+    res->json_bytes = (uint8_t *)ctx->h_json_bytes.p;
+    res->json_off = (uint64_t *)ctx->h_json_off.p;
+    if (!do_path)
+        memset(res->path_off, 0, (n + 1) * 8);
+    if (!do_json)
+        memset(res->json_off, 0, (n + 1) * 8);
+    return REGK_OK;
+}
+
 extern "C" {
 
 int regk_abi_version(void)
@@ -233,7 +444,13 @@ void regk_destroy(regk_ctx *ctx)
     for (DevBuf *b : {&ctx->blob_dev, &ctx->path_bytes, &ctx->path_off, &ctx->json_bytes, &ctx->json_off, &ctx->work})
         if (b->p)
             cudaFree(b->p);
-    for (HostBuf *b : {&ctx->h_path_bytes, &ctx->h_path_off, &ctx->h_json_bytes, &ctx->h_json_off})
+    for (cudaEvent_t e : ctx->pipe_events)
+        cudaEventDestroy(e);
+    if (ctx->s_h2d)
+        cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h)
+        cudaStreamDestroy(ctx->s_d2h);
+    for (HostBuf *b : {&ctx->h_path_bytes, &ctx->h_path_off, &ctx->h_json_bytes, &ctx->h_json_off, &ctx->h_running})
         if (b->p)
             cudaFreeHost(b->p);
     if (ctx->h_status_block)
@@ -261,7 +478,7 @@ int regk_set_option(regk_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name)
         return REGK_ERR_INVALID_ARG;
-    static const char *known[] = {"async", "force_generic", "dom_cap", "json_out_cap", "skip_host_check", nullptr};
+    static const char *known[] = {"async", "force_generic", "dom_cap", "json_out_cap", "chunk_records", nullptr};
     for (const char **k = known; *k; k++)
         if (!strcmp(*k, name)) {
             ctx->opt[name] = value;
@@ -434,6 +651,11 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     if (alias)
         host_len = 0;
 
+    /* Host buffers in and out, large batch: overlap H2D, kernels and D2H chunk by chunk (run_pipelined). */
+    const uint64_t chunk_records = (uint64_t)opt_get(ctx, "chunk_records", 262144) / TILE * TILE;
+    const bool pipelined = !in_dev && !out_dev && !async && chunk_records && n >= 2 * chunk_records &&
+        !opt_get(ctx, "force_generic", 0);
+
     /* ---- inputs on the device ---- */
     const void *src[11] = {b->domain_bytes, b->domain_off, b->host_bytes, b->host_off, b->type_id, b->addr_bytes,
         b->addr_off, b->ttl, b->ports_off, b->ports, b->ports_present};
@@ -454,7 +676,7 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             int rc = ensure_dev(ctx, ctx->in[i], sz[i] + 16);
             if (rc)
                 return rc;
-            if (sz[i])
+            if (sz[i] && !pipelined)
                 CK(cudaMemcpyAsync(ctx->in[i].p, src[i], sz[i], cudaMemcpyHostToDevice, s));
             dev[i] = ctx->in[i].p;
         }
@@ -469,14 +691,17 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         (rc = ensure_dev(ctx, ctx->json_bytes, json_cap)) || (rc = ensure_dev(ctx, ctx->json_off, (n + 1) * 8)))
         return rc;
 
-    /* ---- workspace: status | two-level byte totals of both halves (zeroed with the status) ---- */
+    /* ---- workspace: status | running payload totals per chunk | two-level byte totals of both halves ---- */
     const uint64_t ntiles = (n + TILE - 1) / TILE;
-    const uint64_t nsuper = ntiles / SUPER + 1;
-    const size_t totals_p_off = 128;
+    const uint64_t nchunks = pipelined ? (n + chunk_records - 1) / chunk_records : 1;
+    const uint64_t tiles_per_chunk = pipelined ? chunk_records / TILE : ntiles;
+    const uint64_t nsuper_chunk = tiles_per_chunk / SUPER + 1;
+    const size_t running_off = 128;
+    const size_t totals_p_off = (running_off + (nchunks + 1) * 8 + 15) & ~(size_t)15;
     const size_t super_p_off = (totals_p_off + ntiles * 4 + 15) & ~(size_t)15;
-    const size_t totals_j_off = super_p_off + nsuper * 8;
+    const size_t totals_j_off = super_p_off + nchunks * nsuper_chunk * 8;
     const size_t super_j_off = (totals_j_off + ntiles * 4 + 15) & ~(size_t)15;
-    const size_t work_bytes = super_j_off + nsuper * 8 + 64;
+    const size_t work_bytes = super_j_off + nchunks * nsuper_chunk * 8 + 64;
     if ((rc = ensure_dev(ctx, ctx->work, work_bytes)))
         return rc;
     uint8_t *wk = (uint8_t *)ctx->work.p;
@@ -487,11 +712,52 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         CK(cudaMemsetAsync(ctx->path_off.p, 0, 8, s));
         CK(cudaMemsetAsync(ctx->json_off.p, 0, 8, s));
     }
-    uint32_t launches = 0;
     const uint32_t force_generic = (uint32_t)opt_get(ctx, "force_generic", 0);
-    slot.did_path = false;
-    slot.d_status = d_status;
-    /* payload parameters first: when both halves run, the path kernel also produces the payload tile bases */
+
+    /* ---- kernel parameters for the whole batch ---- */
+    PathParams pp{};
+    size_t path_smem = 0;
+    if (n && do_path) {
+        pp.n = n;
+        pp.domain_bytes = (const uint8_t *)dev[0];
+        pp.domain_off = (const uint32_t *)dev[1];
+        pp.host_bytes = (const uint8_t *)dev[2];
+        pp.host_off = (const uint32_t *)dev[3];
+        pp.host_stride = b->host_stride;
+        pp.out_bytes = (uint8_t *)ctx->path_bytes.p;
+        pp.out_off = (unsigned long long *)ctx->path_off.p;
+        pp.out_capacity = path_cap;
+        pp.exact = 0;                           /* closed-form offsets; see regk_finish for the exact redo */
+        pp.tile_total = (uint32_t *)(wk + totals_p_off);
+        pp.super_total = (unsigned long long *)(wk + super_p_off);
+        pp.status = d_status;
+        pp.dom_limit = dom_len;
+        pp.host_limit = host_len;
+        pp.force_generic = force_generic;
+        /* shared-memory budget: 1.25x the mean tile, clamped; tiles that do not fit go generic */
+        const uint64_t mean_dom_tile = dom_len / std::max<uint64_t>(ntiles, 1) + 1;
+        uint32_t dom_cap = (uint32_t)opt_get(ctx, "dom_cap", 0);
+        if (!dom_cap)
+            dom_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(align16(mean_dom_tile * 5 / 4 + 384), 2048), 49152);
+        dom_cap = (uint32_t)((dom_cap + 127) & ~127u);         /* bitmap region stays 16-byte aligned */
+        uint32_t host_cap = 0;
+        if (!alias) {
+            const uint64_t mean_host_tile = pp.host_off ? host_len / std::max<uint64_t>(ntiles, 1) + 1
+                                                        : (uint64_t)TILE * b->host_stride;
+            host_cap = (uint32_t)std::min<uint64_t>(align16((pp.host_off ? mean_host_tile * 3 / 2 + 512 : mean_host_tile) + 16), 49152);
+        }
+        const uint32_t out_cap = (uint32_t)align16((uint64_t)dom_cap + host_cap + 2 * TILE + 32);
+        path_smem = (size_t)dom_cap + 32 + dom_cap / 8 + 16 + (alias ? 0 : host_cap + 32) + out_cap + 32;
+        if (path_smem > (size_t)ctx->max_smem_optin)
+            return fail(ctx, REGK_ERR_INVALID_ARG, "path kernel needs %zu B of shared memory (> %d)", path_smem, ctx->max_smem_optin);
+        pp.dom_cap = dom_cap;
+        pp.host_cap = host_cap;
+        pp.out_cap = out_cap;
+        if (alias)
+            CK(cudaFuncSetAttribute(regk_path_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
+        else
+            CK(cudaFuncSetAttribute(regk_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
+    }
     JsonParams jp{};
     size_t json_smem = 0;
     if (n && do_json) {
@@ -527,60 +793,45 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         json_smem = (size_t)jp.blob_bytes + out_cap + 32;
         if (json_smem > (size_t)ctx->max_smem_optin)
             return fail(ctx, REGK_ERR_INVALID_ARG, "json kernel needs %zu B of shared memory (> %d)", json_smem, ctx->max_smem_optin);
+        CK(cudaFuncSetAttribute(regk_json_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)json_smem));
     }
+
+    if (pipelined) {
+        HostPipe hp;
+        hp.chunk = chunk_records;
+        hp.nchunks = nchunks;
+        hp.nsuper_chunk = nsuper_chunk;
+        hp.running = (unsigned long long *)(wk + running_off);
+        hp.path_cap = path_cap;
+        hp.json_cap = json_cap;
+        for (int i = 0; i < 11; i++) {
+            hp.src[i] = src[i];
+            hp.dev[i] = need[i] && src[i] ? ctx->in[i].p : nullptr;
+        }
+        rc = run_pipelined(ctx, b, res, pp, path_smem, jp, json_smem, hp);
+        if (rc != REGK_ERR_STATE + 100)         /* anything but "needs the exact redo" */
+            return rc;
+        /* some domain has empty labels: run the whole batch again through the regular (exact-capable) path */
+        for (int i = 0; i < 11; i++)
+            if (dev[i] && sz[i])
+                CK(cudaMemcpyAsync(ctx->in[i].p, src[i], sz[i], cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(wk, 0, work_bytes, s));
+    }
+
+    uint32_t launches = 0;
+    slot.did_path = false;
+    slot.d_status = d_status;
     const bool fused_len = n && do_path && do_json;
-    JsonParams jp_side{};
-    if (fused_len)
-        jp_side = jp;
     CK(cudaEventRecord(slot.ev[0], s));
     if (n && do_path) {
-        PathParams p{};
-        p.n = n;
-        p.domain_bytes = (const uint8_t *)dev[0];
-        p.domain_off = (const uint32_t *)dev[1];
-        p.host_bytes = (const uint8_t *)dev[2];
-        p.host_off = (const uint32_t *)dev[3];
-        p.host_stride = b->host_stride;
-        p.out_bytes = (uint8_t *)ctx->path_bytes.p;
-        p.out_off = (unsigned long long *)ctx->path_off.p;
-        p.out_capacity = path_cap;
-        p.exact = 0;                            /* closed-form offsets; see regk_finish for the exact redo */
-        p.tile_total = (uint32_t *)(wk + totals_p_off);
-        p.super_total = (unsigned long long *)(wk + super_p_off);
-        p.status = d_status;
-        p.dom_limit = dom_len;
-        p.host_limit = host_len;
-        p.force_generic = force_generic;
-        /* shared-memory budget: 1.5x the mean tile, clamped; tiles that do not fit go generic */
-        const uint64_t mean_dom_tile = dom_len / std::max<uint64_t>(ntiles, 1) + 1;
-        uint32_t dom_cap = (uint32_t)opt_get(ctx, "dom_cap", 0);
-        if (!dom_cap)
-            dom_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(align16(mean_dom_tile * 5 / 4 + 384), 2048), 49152);
-        dom_cap = (uint32_t)((dom_cap + 127) & ~127u);         /* bitmap region stays 16-byte aligned */
-        uint32_t host_cap = 0;
-        if (!alias) {
-            const uint64_t mean_host_tile = p.host_off ? host_len / std::max<uint64_t>(ntiles, 1) + 1
-                                                       : (uint64_t)TILE * b->host_stride;
-            host_cap = (uint32_t)std::min<uint64_t>(align16((p.host_off ? mean_host_tile * 3 / 2 + 512 : mean_host_tile) + 16), 49152);
-        }
-        uint32_t out_cap = (uint32_t)align16((uint64_t)dom_cap + host_cap + 2 * TILE + 32);
-        size_t smem = (size_t)dom_cap + 32 + dom_cap / 8 + 16 + (alias ? 0 : host_cap + 32) + out_cap + 32;
-        if (smem > (size_t)ctx->max_smem_optin)
-            return fail(ctx, REGK_ERR_INVALID_ARG, "path kernel needs %zu B of shared memory (> %d)", smem, ctx->max_smem_optin);
-        p.dom_cap = dom_cap;
-        p.host_cap = host_cap;
-        p.out_cap = out_cap;
-        if (alias) {
-            CK(cudaFuncSetAttribute(regk_path_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            regk_path_kernel<true><<<(unsigned)ntiles, TILE, smem, s>>>(p, jp_side);
-        } else {
-            CK(cudaFuncSetAttribute(regk_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            regk_path_kernel<false><<<(unsigned)ntiles, TILE, smem, s>>>(p, jp_side);
-        }
+        if (alias)
+            regk_path_kernel<true><<<(unsigned)ntiles, TILE, path_smem, s>>>(pp, fused_len ? jp : JsonParams{});
+        else
+            regk_path_kernel<false><<<(unsigned)ntiles, TILE, path_smem, s>>>(pp, fused_len ? jp : JsonParams{});
         CK(cudaGetLastError());
         launches++;
-        slot.path_params = p;
-        slot.path_smem = smem;
+        slot.path_params = pp;
+        slot.path_smem = path_smem;
         slot.path_alias = alias;
         slot.did_path = true;
     }
@@ -593,7 +844,6 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             launches++;
         }
         CK(cudaEventRecord(slot.ev[2], s));
-        CK(cudaFuncSetAttribute(regk_json_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)json_smem));
         regk_json_kernel<<<(unsigned)ntiles, TILE, json_smem, s>>>(jp);
         CK(cudaGetLastError());
         launches++;

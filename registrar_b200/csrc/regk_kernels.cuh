@@ -230,6 +230,9 @@ struct JsonParams {
     uint8_t *out_bytes;
     unsigned long long *out_off;
     uint64_t out_capacity;
+    uint64_t rec0;                      /* index of this chunk's first record in the caller's batch (error reports) */
+    const unsigned long long *base_in;  /* optional: payload bytes of all earlier chunks (host pipelining) */
+    unsigned long long *base_out;       /* optional: *base_in + this chunk's payload bytes */
     uint32_t *tile_total;               /* [ntiles] payload bytes per tile, accumulated by the producer kernel */
     unsigned long long *super_total;    /* [ntiles / SUPER + 1] */
     DevStatus *status;
@@ -303,6 +306,9 @@ struct PathParams {
     uint8_t *out_bytes;
     unsigned long long *out_off;        /* [n+1] */
     uint64_t out_capacity;
+    uint64_t rec0;                      /* index of this chunk's first record in the caller's batch (error reports) */
+    uint64_t off_bias;                  /* added to every output offset: a chunk of a larger batch keeps absolute
+                                           input offsets but numbers its records from 0 (host pipelining) */
     uint32_t exact;                     /* 0: closed-form offsets; 1: bases from tile_total / super_total */
     uint32_t *tile_total;               /* [ntiles]   exact path bytes per tile (regk_path_len_kernel) */
     unsigned long long *super_total;    /* [ntiles / SUPER + 1] */
@@ -448,7 +454,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         const bool tile_broken = D1 < D0 || D1 > p.dom_limit || (!ALIAS && (HB1 < HB0 || HB1 > p.host_limit));
         if (__syncthreads_or(rec_broken || tile_broken)) {
             if (live && (rec_broken || tile_broken))
-                report_bad(p.status, BAD_TOO_LARGE, r);
+                report_bad(p.status, BAD_TOO_LARGE, p.rec0 + r);
             if (side)
                 payload_length_side_job(jp, jm, jtf, live, tile);
             return;
@@ -461,7 +467,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
     if (!exact) {
         const unsigned long long cf0 = (unsigned long long)D0 + (ALIAS ? r0 : HB0 + 2ull * r0);
         const unsigned long long cf1 = (unsigned long long)D1 + (ALIAS ? r0 + nrec : HB1 + 2ull * (r0 + nrec));
-        tile_base = cf0;
+        tile_base = cf0 + p.off_bias;
         tile_total = (uint32_t)(cf1 - cf0);
         local = (uint32_t)(((unsigned long long)d0 + (ALIAS ? r : h0 + 2ull * r)) - cf0);
         slot = ALIAS ? L + 1u : L + 2u + H;
@@ -473,7 +479,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
                 s_exact_base = b;
         }
         __syncthreads();
-        tile_base = s_exact_base;
+        tile_base = s_exact_base + p.off_bias;
         tile_total = p.tile_total[tile];
     }
 
@@ -557,7 +563,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         }
     }
     if (live)
-        report_bad(p.status, bad, r);
+        report_bad(p.status, bad, p.rec0 + r);
     if (r0 + nrec == p.n && t == 0) {
         p.out_off[p.n] = tile_base + tile_total;
         p.status->path_total = tile_base + tile_total;
@@ -618,7 +624,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const J
     if (t < 32) {                                               /* warp 0: this tile's base from the two-level totals */
         const unsigned long long b = tile_base_from_totals(p.tile_total, p.super_total, tile);
         if (t == 0)
-            s_base = b;
+            s_base = b + (p.base_in ? *p.base_in : 0ull);
     }
     const uint32_t tile_total = p.tile_total[tile];
 
@@ -684,10 +690,12 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const J
         emit_json(blob, tf, aw, asrc, a0, al, m.has_ttl, m.ttl, m.has_ports, k, port, sink);
     }
     if (live)
-        report_bad(p.status, bad, r);
+        report_bad(p.status, bad, p.rec0 + r);
     if (r0 + nrec == p.n && t == 0) {
         p.out_off[p.n] = tile_base + tile_total;
         p.status->json_total = tile_base + tile_total;
+        if (p.base_out)
+            *p.base_out = tile_base + tile_total;
     }
 }
 

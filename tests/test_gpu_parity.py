@@ -51,7 +51,7 @@ def test_config2_full_size(ctx):
     batch = synth.generate("config2")
     got = ctx.register_batch(batch)
     assert_same(got, oracle.register_batch(batch))
-    assert got.launches == 2          # path (+ payload lengths as a side job), payload
+    assert got.launches == 2 * 4      # host buffers: 4 pipelined chunks x (path + payload-length side job, payload)
 
 
 @pytest.mark.parametrize("start", [1, 7, 255, 1001, 99_999_999_000])
@@ -233,3 +233,58 @@ def test_corrupt_offsets_are_refused_not_dereferenced(ctx):
         assert ei.value.result.bad_bits & BAD_TOO_LARGE
         setattr(batch, field, saved)
     assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
+
+
+# ---- host pipelining (chunked H2D | kernels | D2H overlap inside regk_register_batch) -----------------
+
+@pytest.fixture()
+def small_chunks(ctx):
+    ctx.set_option("chunk_records", 512)
+    yield ctx
+    ctx.set_option("chunk_records", 262144)
+
+
+@pytest.mark.parametrize("config,n", [("config1", 1024), ("config3", 5000), ("config5", 4097), ("config2", 1536)])
+def test_pipelined_chunks_equal_the_oracle(small_chunks, config, n):
+    batch = synth.generate(config, n=n, start=12345)
+    got = small_chunks.register_batch(batch)
+    assert got.launches >= 2 * (n // 512)            # really went chunk by chunk
+    assert_same(got, oracle.register_batch(batch))
+
+
+def test_pipelined_variable_hostnames_alias_and_halves(small_chunks):
+    recs = [{"domain": b"a%d.b%d.c" % (i, i % 7), "hostname": b"h" * (1 + i % 40), "type": b"host",
+             "address": b"10.0.%d.%d" % (i % 200, i % 250), "ttl": [None, 30, 86400][i % 3],
+             "ports": [None, [80], [1, 65535, 443]][i % 3]} for i in range(3000)]
+    batch = RecordBatch.from_records(recs)
+    assert batch.host_off is not None
+    want = oracle.register_batch(batch)
+    assert_same(small_chunks.register_batch(batch), want)
+    got = small_chunks.register_batch(batch, payloads=False)
+    assert np.array_equal(got.path_bytes, want.path_bytes) and np.array_equal(got.path_off, want.path_off)
+    got = small_chunks.register_batch(batch, paths=False)
+    assert np.array_equal(got.json_bytes, want.json_bytes) and np.array_equal(got.json_off, want.json_off)
+    alias = RecordBatch.from_records(recs, alias=True)
+    assert_same(small_chunks.register_batch(alias), oracle.register_batch(alias))
+
+
+def test_pipelined_empty_labels_fall_back_to_the_exact_path(small_chunks):
+    recs = [{"domain": b"svc%d.example.com" % i, "hostname": b"h%04d" % i, "type": b"host", "address": b"10.0.0.1"}
+            for i in range(4000)]
+    recs[2777]["domain"] = b".a..b."
+    batch = RecordBatch.from_records(recs)
+    got = small_chunks.register_batch(batch)
+    assert_same(got, oracle.register_batch(batch))
+    assert got.path(2777) == b"/b/a/h2777"
+
+
+def test_pipelined_errors_carry_global_record_indices(small_chunks):
+    from registrar_b200._native import OutOfDomainError
+    recs = [{"domain": b"svc%d.example.com" % i, "hostname": b"h", "type": b"host", "address": b"10.0.0.1"}
+            for i in range(3000)]
+    recs[2100]["address"] = b'1"2'
+    recs[2900]["domain"] = b"x/y"
+    with pytest.raises(OutOfDomainError) as ei:
+        small_chunks.register_batch(RecordBatch.from_records(recs))
+    assert ei.value.result.first_bad == 2100
+    assert ei.value.result.bad_bits == (BAD_ADDR_BYTE | BAD_DOMAIN_BYTE)
