@@ -143,23 +143,22 @@ RG_HD uint32_t lower7(uint32_t v7)
  * There is no per-store branch on "is this the first word".
  */
 struct WordSink {
-    uint32_t *words;        /* image base (word aligned) */
-    uint32_t wi;            /* index of the word being filled */
+    uint32_t *wp;           /* the word being filled */
     uint32_t carry;         /* its bytes so far (low `s` bits) */
     uint32_t s;             /* pending bits: 0, 8, 16 or 24 */
-    uint32_t wi0, h0;       /* first word and the number of foreign bytes in it */
+    uint32_t *wp0;          /* first word of the record ... */
+    uint32_t h0;            /* ... and the number of foreign bytes in it */
 
     RG_HD void init(uint32_t *base, uint32_t byte_off)
     {
-        words = base;
-        wi = wi0 = byte_off >> 2;
+        wp = wp0 = base + (byte_off >> 2);
         h0 = byte_off & 3u;
         s = h0 * 8u;
         carry = 0;
     }
     RG_HD void put4(uint32_t v)
     {
-        words[wi++] = carry | (v << s);
+        *wp++ = carry | (v << s);
         carry = funnel_rc(v, 0u, 32u - s);
     }
     /* append the low n bytes of v (1 <= n <= 4); bytes of v above n must be zero */
@@ -167,22 +166,29 @@ struct WordSink {
     {
         const uint32_t out = carry | (v << s);
         const uint32_t ns = s + 8u * n;
-        if (ns >= 32u) {
-            words[wi++] = out;
-            carry = funnel_rc(v, 0u, 32u - s);
-            s = ns - 32u;
-        } else {
-            carry = out;
-            s = ns;
-        }
+        const bool full = ns >= 32u;
+        if (full)
+            *wp = out;
+        wp += full ? 1 : 0;
+        carry = full ? funnel_rc(v, 0u, 32u - s) : out;
+        s = full ? ns - 32u : ns;
     }
-    RG_HD void put1(uint32_t c) { put(c, 1); }
+    RG_HD void put1(uint32_t c)
+    {
+        const uint32_t out = carry | (c << s);
+        const bool full = s == 24u;
+        if (full)
+            *wp = out;
+        wp += full ? 1 : 0;
+        carry = full ? 0u : out;
+        s = full ? 0u : s + 8u;
+    }
     RG_HD void finish() {}
     /* phase B: after every thread of the tile has finished phase A */
     RG_HD void tail()
     {
-        uint8_t *b = reinterpret_cast<uint8_t *>(words + wi);
-        const uint32_t lo = (wi == wi0) ? h0 : 0u;
+        uint8_t *b = reinterpret_cast<uint8_t *>(wp);
+        const uint32_t lo = (wp == wp0) ? h0 : 0u;
         const uint32_t hi = s >> 3;
         if (lo <= 0u && hi > 0u)
             b[0] = (uint8_t)carry;
@@ -419,9 +425,11 @@ RG_HD uint32_t movemask4(uint32_t m)
 /*
  * Domain pre-pass over the staged bytes of a tile, 16 bytes per step, thread t of
  * nt takes chunks t, t+nt, ...: lower-cases ASCII letters in place (A1,
- * toLowerCase), records one "is '.'" bit per byte in `bits` (16 bits per chunk) and
- * returns nonzero if a byte outside the fence (>= 0x80 or '/') was seen anywhere in
- * the chunks it handled — the caller then re-validates record by record.
+ * toLowerCase), records one "is '.'" bit per byte in `bits` (16 bits per chunk),
+ * rewrites every '.' to '/' in place (so a label can be copied together with the
+ * separator in front of it) and returns nonzero if a byte outside the fence
+ * (>= 0x80 or '/') was seen anywhere in the chunks it handled — the caller then
+ * re-validates record by record (recheck_domain).
  */
 RG_HD uint32_t prepass_domain(uint32_t *dom_words, uint16_t *bits, uint32_t nchunks, uint32_t t, uint32_t nt)
 {
@@ -436,7 +444,7 @@ RG_HD uint32_t prepass_domain(uint32_t *dom_words, uint16_t *bits, uint32_t nchu
             const uint32_t dot = zero7(x);
             slash |= dot ^ zero7(x & 0x7E7E7E7Eu);
             hib |= w;
-            dom_words[4 * c + j] = lower7(v7) | (w & 0x80808080u);
+            dom_words[4 * c + j] = lower7(v7) | (w & 0x80808080u) | (dot >> 7);    /* 0x2e | 1 = 0x2f */
             m |= movemask4(dot) << (4 * j);
         }
         bits[c] = (uint16_t)m;
@@ -444,20 +452,32 @@ RG_HD uint32_t prepass_domain(uint32_t *dom_words, uint16_t *bits, uint32_t nchu
     return (hib & 0x80808080u) | slash;
 }
 
-/* Hostname pre-pass: nonzero if any staged byte is >= 0x80, NUL or '/'. */
+/* Hostname pre-pass: nonzero if any staged byte is >= 0x80, NUL or '/'.  Uses the borrow-based "has a zero
+ * byte" test ((v - 0x01..) & ~v & 0x80..), which is exact as a yes/no answer over the word. */
 RG_HD uint32_t prepass_host(const uint32_t *host_words, uint32_t nchunks, uint32_t t, uint32_t nt)
 {
-    uint32_t hib = 0, hit = 0;
+    uint32_t acc = 0;
     for (uint32_t c = t; c < nchunks; c += nt) {
         #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t w = host_words[4 * c + j];
-            const uint32_t v7 = w & 0x7F7F7F7Fu;
-            hib |= w;
-            hit |= eq7(v7, 0x2F) | zero7(v7);
+            const uint32_t x = w ^ 0x2F2F2F2Fu;
+            acc |= w | ((w - 0x01010101u) & ~w) | ((x - 0x01010101u) & ~x);
         }
     }
-    return (hib & 0x80808080u) | hit;
+    return acc & 0x80808080u;
+}
+
+/* exact per-record domain fence on pre-passed bytes (dots already rewritten to '/'): rare path */
+RG_HD uint32_t recheck_domain(const uint8_t *dom, const uint32_t *bits, uint32_t doff, uint32_t L)
+{
+    for (uint32_t i = 0; i < L; i++) {
+        const uint32_t c = dom[doff + i], b = doff + i;
+        const bool is_dot = (bits[b >> 5] >> (b & 31u)) & 1u;
+        if (c >= 0x80u || (c == 0x2Fu && !is_dot))
+            return BAD_DOMAIN_BYTE;
+    }
+    return 0;
 }
 
 /* What the path needs to know about one domain, from the dot bitmap. */
@@ -512,84 +532,145 @@ RG_HD uint32_t path_length2(const DomainInfo &di, uint32_t L, uint32_t H, bool a
     return alias ? L + 1u : 1u + di.nondot + di.labels + H;
 }
 
-/* plain copy (bytes already lower-cased by the pre-pass) */
-template <class Src, class Sink>
-RG_HD void copy_plain(const Src &src, uint32_t off, uint32_t len, Sink &sink)
+/* 16 bytes starting at byte offset `off` of a padded word buffer -> 4 registers (5 loads, 4 funnel shifts) */
+RG_HD void load16(const uint32_t *w, uint32_t off, uint32_t (&a)[4])
 {
-    if (len == 0)
-        return;
-    uint32_t wi = off >> 2;
+    const uint32_t *p = w + (off >> 2);
     const uint32_t sh = (off & 3u) * 8u;
-    uint32_t lo = src.word(wi);
-    while (len >= 4) {
-        const uint32_t hi = src.word_hi(wi + 1, sh != 0 || len > 4);
-        sink.put4(funnel_r(lo, hi, sh));
-        lo = hi;
-        wi++;
-        len -= 4;
-    }
-    if (len) {
-        const uint32_t hi = src.word_hi(wi + 1, sh + 8 * len > 32);
-        sink.put(funnel_r(lo, hi, sh) & low_bytes(len), len);
-    }
+    const uint32_t w0 = p[0], w1 = p[1], w2 = p[2], w3 = p[3], w4 = p[4];
+    a[0] = funnel_r(w0, w1, sh);
+    a[1] = funnel_r(w1, w2, sh);
+    a[2] = funnel_r(w2, w3, sh);
+    a[3] = funnel_r(w3, w4, sh);
 }
 
 /*
- * Emit one znode path from pre-passed inputs (see emit_path for the semantics).
- * Label boundaries come from the dot bitmap (one clz per label) when the domain is
- * at most 64 bytes; longer domains fall back to scanning the bytes.  The hostname is
- * copied word for word when it is 4-byte aligned and a multiple of 4 bytes long
- * (36-byte UUIDs at a fixed stride always are).
+ * Append the first n (1..16) bytes of a 16-byte register block; bytes of a[] beyond n may be anything.
+ *
+ * OVERSHOOT = true: straight-line code — the five candidate words are all stored and the new carry is read
+ * back from the word that stays open.  Up to 20 bytes past the sink's current word are overwritten with
+ * garbage, so it may only be used while at least 24 more bytes of the SAME record follow (they are written
+ * later by this thread, and the record's last, possibly shared, word is never touched).
+ * OVERSHOOT = false: exact stores, for the end of a record.
  */
-template <bool ALIAS, class DSrc, class HSrc, class Sink>
-RG_HD void emit_path2(const DSrc &dsrc, uint32_t doff, uint32_t L, const DomainInfo &di, const HSrc &hsrc,
-    uint32_t hoff, uint32_t H, Sink &sink)
+template <bool OVERSHOOT>
+RG_HD void put_block16(const uint32_t (&a)[4], uint32_t n, WordSink &sink)
 {
-    if (di.small) {
-        uint32_t e = L;                                     /* end (exclusive) of the current label, relative */
-        for (;;) {
-            const uint64_t below = e >= 64u ? di.dots : (di.dots & ((1ull << e) - 1ull));
-            const uint32_t s = 64u - clz64(below);          /* position after the last '.' below e, or 0 */
-            if (ALIAS || e > s) {
-                sink.put1('/');
-                copy_plain(dsrc, doff + s, e - s, sink);
-            }
-            if (s == 0)
-                break;
-            e = s - 1;
-        }
+    const uint32_t sh = sink.s, back = 32u - sh;
+    const uint32_t o0 = sink.carry | (a[0] << sh);
+    const uint32_t o1 = funnel_rc(a[0], a[1], back);
+    const uint32_t o2 = funnel_rc(a[1], a[2], back);
+    const uint32_t o3 = funnel_rc(a[2], a[3], back);
+    const uint32_t o4 = funnel_rc(a[3], 0u, back);
+    const uint32_t total = (sh >> 3) + n;
+    const uint32_t nfull = total >> 2, rem = total & 3u;
+    uint32_t *dst = sink.wp;
+    uint32_t c;
+    if (OVERSHOOT) {
+        dst[0] = o0;
+        dst[1] = o1;
+        dst[2] = o2;
+        dst[3] = o3;
+        dst[4] = o4;
+        c = dst[nfull];
     } else {
-        uint32_t e = doff + L;
-        for (;;) {
-            const int32_t dot = e > doff ? find_prev_dot(dsrc, doff, e) : (int32_t)doff - 1;
-            const uint32_t s = (uint32_t)(dot + 1);
-            if (ALIAS || e > s) {
-                sink.put1('/');
-                copy_plain(dsrc, s, e - s, sink);
-            }
-            if (s == doff)
-                break;
-            e = s - 1;
+        if (nfull > 0) dst[0] = o0;
+        if (nfull > 1) dst[1] = o1;
+        if (nfull > 2) dst[2] = o2;
+        if (nfull > 3) dst[3] = o3;
+        c = nfull == 0 ? o0 : nfull == 1 ? o1 : nfull == 2 ? o2 : nfull == 3 ? o3 : o4;
+    }
+    sink.carry = c & low_bytes(rem);
+    sink.wp = dst + nfull;
+    sink.s = rem * 8u;
+}
+
+/* copy len bytes from a padded word buffer in 16-byte register blocks */
+template <bool OVERSHOOT>
+RG_HD void copy_blocks(const uint32_t *w, uint32_t off, uint32_t len, WordSink &sink)
+{
+    uint32_t a[4];
+    while (len) {
+        const uint32_t n = len < 16u ? len : 16u;
+        load16(w, off, a);
+        put_block16<OVERSHOOT>(a, n, sink);
+        off += 16u;
+        len -= n;
+    }
+}
+
+/* position after the last '.' strictly below relative position e of the domain whose bit 0 is bitmap bit b0, or 0 */
+RG_HD uint32_t label_start_below(const uint32_t *bits, uint32_t b0, uint32_t e)
+{
+    uint32_t pos = b0 + e;                                  /* absolute bit index, exclusive */
+    while (pos > b0) {
+        const uint32_t wi = (pos - 1u) >> 5;
+        uint32_t w = bits[wi];
+        const uint32_t top = pos - (wi << 5);               /* 1..32 bits of this word are below pos */
+        if (top < 32u)
+            w &= (1u << top) - 1u;
+        const uint32_t base = wi << 5;
+        if (base < b0)
+            w &= ~((1u << (b0 - base)) - 1u);
+        if (w)
+            return base + 32u - clz32(w) - b0;
+        if (base <= b0)
+            break;
+        pos = base;
+    }
+    return 0;
+}
+
+/*
+ * Emit one znode path from pre-passed shared-memory inputs (see emit_path for the semantics).
+ * `dom` holds lower-cased bytes with every '.' already rewritten to '/', so a label that does not start
+ * the domain is copied together with the separator in front of it ('/' + label in one block copy); only
+ * the label at offset 0 and the hostname need an explicit '/'.  Label boundaries come from the dot bitmap
+ * (one clz per label for domains up to 64 bytes, a backward word scan of the bitmap beyond that).
+ * FAST: a hostname of >= 24 bytes follows the labels, so label blocks may overshoot (put_block16).
+ */
+template <bool ALIAS, bool FAST>
+RG_HD void emit_path2(const uint32_t *dom, const uint32_t *bits, uint32_t doff, uint32_t L, const DomainInfo &di,
+    const uint32_t *host, uint32_t hoff, uint32_t H, WordSink &sink)
+{
+    uint32_t e = L;                                         /* end (exclusive) of the current label, relative */
+    for (;;) {
+        uint32_t s;
+        if (di.small) {
+            const uint64_t below = e >= 64u ? di.dots : (di.dots & ((1ull << e) - 1ull));
+            s = 64u - clz64(below);                         /* position after the last '.' below e, or 0 */
+        } else {
+            s = label_start_below(bits, doff, e);
         }
+        if (ALIAS || e > s) {
+            const uint32_t lead = s > 0 ? 1u : 0u;          /* the separator in front of the label comes along */
+            if (!lead)
+                sink.put1('/');
+            copy_blocks<FAST>(dom, doff + s - lead, e - s + lead, sink);
+        }
+        if (s == 0)
+            break;
+        e = s - 1u;
     }
     if (!ALIAS) {
         sink.put1('/');
         if (((hoff | H) & 3u) == 0) {
-            const uint32_t w0 = hoff >> 2, nw = H >> 2;
+            const uint32_t *hw = host + (hoff >> 2);
+            const uint32_t nw = H >> 2;
             if (nw == 9) {                                  /* 36-byte UUID: all loads in flight, then the stores */
                 uint32_t h[9];
                 #pragma unroll
                 for (int i = 0; i < 9; i++)
-                    h[i] = hsrc.word(w0 + i);
+                    h[i] = hw[i];
                 #pragma unroll
                 for (int i = 0; i < 9; i++)
                     sink.put4(h[i]);
             } else {
                 for (uint32_t i = 0; i < nw; i++)
-                    sink.put4(hsrc.word(w0 + i));
+                    sink.put4(hw[i]);
             }
         } else {
-            copy_plain(hsrc, hoff, H, sink);
+            copy_blocks<false>(host, hoff, H, sink);
         }
     }
 }
@@ -706,36 +787,76 @@ RG_HD void put_frag(const Src &blob, uint32_t off, uint32_t len, Sink &sink)
     put_aligned(blob, off, len, sink);
 }
 
-/* word sink: copy from the variant that matches the sink's byte phase */
-template <class Src>
-RG_HD void put_frag(const Src &blob, uint32_t off, uint32_t len, WordSink &sink)
+/*
+ * word sink: copy from the variant that matches the sink's byte phase.
+ * OVERSHOOT = true copies a fixed MAXW words with no loop and no bounds (garbage lands in the next <= 16
+ * bytes, which the caller guarantees belong to the same record and are written later);
+ * OVERSHOOT = false stores exactly the completed words.
+ */
+template <bool OVERSHOOT, uint32_t MAXW, class Src>
+RG_HD void put_frag_w(const Src &blob, uint32_t off, uint32_t len, WordSink &sink)
 {
     const uint32_t ph = sink.s >> 3;
     const uint32_t src = (off >> 2) + ph * frag_stride_words(len);
     const uint32_t total = ph + len;
     const uint32_t nfull = total >> 2, rem = total & 3u;
+    uint32_t *dst = sink.wp;
     const uint32_t first = blob.word(src) | sink.carry;
-    if (nfull == 0) {
-        sink.carry = first;
-        sink.s = total * 8u;
-        return;
+    if (OVERSHOOT) {
+        uint32_t v[MAXW];
+        #pragma unroll
+        for (uint32_t i = 1; i < MAXW; i++)
+            v[i] = blob.word(src + i);
+        dst[0] = first;
+        #pragma unroll
+        for (uint32_t i = 1; i < MAXW; i++)
+            dst[i] = v[i];
+        sink.carry = rem ? (nfull ? blob.word(src + nfull) : first) : 0u;
+    } else {
+        if (nfull == 0) {
+            sink.carry = first;
+            sink.s = total * 8u;
+            return;
+        }
+        dst[0] = first;
+        uint32_t i = 1;
+        for (; i + 4 <= nfull; i += 4) {                    /* loads first: 4 independent LDS in flight */
+            const uint32_t a = blob.word(src + i), b = blob.word(src + i + 1), c = blob.word(src + i + 2),
+                           d = blob.word(src + i + 3);
+            dst[i] = a;
+            dst[i + 1] = b;
+            dst[i + 2] = c;
+            dst[i + 3] = d;
+        }
+        for (; i < nfull; i++)
+            dst[i] = blob.word(src + i);
+        sink.carry = rem ? blob.word(src + nfull) : 0u;
     }
-    uint32_t *dst = sink.words + sink.wi;
-    dst[0] = first;
-    uint32_t i = 1;
-    for (; i + 4 <= nfull; i += 4) {                        /* loads first: 4 independent LDS in flight */
-        const uint32_t a = blob.word(src + i), b = blob.word(src + i + 1), c = blob.word(src + i + 2),
-                       d = blob.word(src + i + 3);
-        dst[i] = a;
-        dst[i + 1] = b;
-        dst[i + 2] = c;
-        dst[i + 3] = d;
-    }
-    for (; i < nfull; i++)
-        dst[i] = blob.word(src + i);
-    sink.wi += nfull;
-    sink.carry = rem ? blob.word(src + nfull) : 0u;
+    sink.wp = dst + nfull;
     sink.s = rem * 8u;
+}
+
+template <class Src>
+RG_HD void put_frag(const Src &blob, uint32_t off, uint32_t len, WordSink &sink)
+{
+    put_frag_w<false, 1>(blob, off, len, sink);
+}
+
+/* The opening fragment {"type":"T","address":" : at least 24 more bytes of the record always follow it
+ * (address, quote, second fragment, address, "}}), so up to 37 bytes it is copied as 10 unconditional words. */
+template <class Src, class Sink>
+RG_HD void put_frag_first(const Src &blob, uint32_t off, uint32_t len, Sink &sink)
+{
+    put_frag(blob, off, len, sink);
+}
+
+template <class Src>
+RG_HD void put_frag_first(const Src &blob, uint32_t off, uint32_t len, WordSink &sink)
+{
+    if (len <= 37u)
+        put_frag_w<true, 10>(blob, off, len, sink);
+    else
+        put_frag_w<false, 1>(blob, off, len, sink);
 }
 
 /* the first (up to) 16 address bytes, from registers (bytes of aw[] beyond n are zero) */
@@ -762,13 +883,13 @@ RG_HD void put_addr16(const uint32_t (&aw)[4], uint32_t n, WordSink &sink)
     const uint32_t o4 = funnel_rc(aw[3], 0u, back);
     const uint32_t total = (sh >> 3) + n;
     const uint32_t nfull = total >> 2;                      /* 0..4 */
-    uint32_t *dst = sink.words + sink.wi;
+    uint32_t *dst = sink.wp;
     if (nfull > 0) dst[0] = o0;
     if (nfull > 1) dst[1] = o1;
     if (nfull > 2) dst[2] = o2;
     if (nfull > 3) dst[3] = o3;
     sink.carry = nfull == 0 ? o0 : nfull == 1 ? o1 : nfull == 2 ? o2 : nfull == 3 ? o3 : o4;
-    sink.wi += nfull;
+    sink.wp = dst + nfull;
     sink.s = (total & 3u) * 8u;
 }
 
@@ -800,7 +921,7 @@ RG_HD void emit_json(const FSrc &blob, const TypeFrag &tf, const uint32_t (&aw)[
     Sink &sink)
 {
     const uint32_t a16 = al < 16u ? al : 16u;
-    put_frag(blob, tf.f1_off, tf.f1_len, sink);             /* {"type":"T","address":" */
+    put_frag_first(blob, tf.f1_off, tf.f1_len, sink);       /* {"type":"T","address":" */
     put_addr16(aw, a16, sink);
     if (al > 16u)
         copy_bytes<false>(asrc, aoff + 16u, al - 16u, sink);

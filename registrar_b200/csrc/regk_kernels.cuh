@@ -78,23 +78,56 @@ __device__ __forceinline__ void stg_v4(void *p, const uint4 &v)
                  ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+/* ---- TMA bulk copy + mbarrier primitives (SASS UBLKCP / SYNCS) ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
 /*
- * Stage the global byte range [g0, g1) of `src` (16-byte aligned base) into shared
- * memory so that global byte g lands at smem byte g - (g0 & ~15).  `limit` is the
- * total number of valid bytes behind `src`; 16-byte chunks reaching past it are
- * loaded byte by byte so nothing outside the caller's buffer is touched.
+ * Manual staging (only for the last blocks of a stream, where whole 16-byte blocks would reach past the
+ * caller's buffer): global byte range [g0, g1) of `src` (16-byte aligned base) -> shared memory so that
+ * global byte g lands at smem byte g - (g0 & ~15); bytes at or past `limit` are not touched (zero filled).
  */
 __device__ __forceinline__ void stage_in(uint8_t *smem, const uint8_t *src, uint64_t g0, uint64_t g1,
     uint64_t limit)
 {
     const uint64_t a0 = g0 & ~15ull;
-    for (uint64_t c = a0 + 16ull * threadIdx.x; c < g1; c += 16ull * TILE) {
-        uint8_t *d = smem + (c - a0);
-        if (c + 16 <= limit) {
-            *reinterpret_cast<uint4 *>(d) = ldg_nc_v4(src + c);
+    const uint8_t *base = src + a0;
+    const uint32_t nchunks = (uint32_t)((g1 - a0 + 15) >> 4);
+    const uint32_t safe = limit > a0 ? (uint32_t)min((uint64_t)nchunks, (limit - a0) >> 4) : 0u;   /* fully inside the buffer */
+    for (uint32_t c = threadIdx.x; c < nchunks; c += TILE) {
+        if (c < safe) {
+            reinterpret_cast<uint4 *>(smem)[c] = ldg_nc_v4(base + 16u * c);
         } else {
-            for (int k = 0; k < 16; k++)
-                d[k] = (c + k < limit) ? src[c + k] : (uint8_t)0;
+            for (uint32_t k = 0; k < 16; k++)
+                smem[16u * c + k] = (a0 + 16ull * c + k < limit) ? base[16u * c + k] : (uint8_t)0;
         }
     }
 }
@@ -375,67 +408,64 @@ __device__ __forceinline__ void payload_length_side_job(const JsonParams &jp, co
 }
 
 /*
- * `jp.n != 0` turns on a side job: this kernel also computes the PAYLOAD length of each of its records
- * (metadata only; the loads overlap the staging of the path inputs) and adds the per-warp sums into
- * jp.tile_total / jp.super_total, from which every CTA of regk_json_kernel derives its base — no separate
- * pass over the payload metadata and no scan launch.
+ * regk_path_kernel: one CTA per tile of TILE records.
+ *  - tile inputs (contiguous byte ranges of domain_bytes / host_bytes) are staged into shared memory by two
+ *    cp.async.bulk copies (TMA engine) issued by one thread, completion on an mbarrier — no per-thread
+ *    staging instructions;
+ *  - `jp.n != 0` turns on a side job: the kernel also computes the PAYLOAD length of each of its records
+ *    (metadata only; those loads overlap the staging) and adds the per-warp sums into jp.tile_total /
+ *    jp.super_total, from which every CTA of regk_json_kernel derives its base — no separate pass over the
+ *    payload metadata and no scan launch.
  */
 template <bool ALIAS>
 __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const PathParams p, const JsonParams jp)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t warp_sum[WARPS];
-    uint8_t *s_dom = smem;                                      /* staged domain bytes, lower-cased in place */
-    uint8_t *s_bits = s_dom + p.dom_cap + 32;                   /* 1 bit per staged domain byte: is '.' */
+    __shared__ __align__(8) uint64_t s_bar;
+    uint8_t *s_dom = smem;                                      /* staged domain bytes: lower-cased, '.' -> '/' */
+    uint8_t *s_bits = s_dom + p.dom_cap + 32;                   /* 1 bit per staged domain byte: was '.' */
     uint8_t *s_host = s_bits + p.dom_cap / 8 + 16;
     uint8_t *s_out = s_host + (ALIAS ? 0 : p.host_cap + 32);
 
     const uint32_t tile = blockIdx.x;
+    const uint32_t t = threadIdx.x;
+    if (t == 0)
+        mbar_init(&s_bar, 1);
     const uint64_t r0 = (uint64_t)tile * TILE;
     const uint32_t nrec = (uint32_t)min((uint64_t)TILE, p.n - r0);
-    const uint32_t t = threadIdx.x;
     const bool live = t < nrec;
-    const uint64_t r = r0 + (live ? t : 0);
+    const uint32_t tl = live ? t : 0u;                          /* idle threads shadow record 0 of the tile */
+    const uint64_t r = r0 + tl;
     const bool exact = p.exact != 0;
+    const bool var_host = !ALIAS && p.host_off != nullptr;
 
-    /* per-record extents */
-    uint32_t d0 = p.domain_off[r], d1 = p.domain_off[r + 1];
-    uint32_t bad = 0;
-    if (d1 < d0) {
-        bad |= BAD_TOO_LARGE;
-        d1 = d0;
-    }
-    uint32_t L = live ? d1 - d0 : 0;
-    uint64_t h0 = 0;
-    uint32_t H = 0;
+    /* ---- extents: the tile's (uniform) and this record's, relative to the tile wherever possible ---- */
+    const uint32_t D0 = p.domain_off[r0], D1 = p.domain_off[r0 + nrec];
+    const uint32_t d0 = p.domain_off[r], d1 = p.domain_off[r + 1];
+    uint64_t HB0 = 0, HB1 = 0;                                  /* tile extent in host_bytes */
+    uint32_t hrel = 0, H = 0;                                   /* record: offset from HB0, length */
+    bool rec_broken = d1 < d0 || d0 < D0 || d1 > D1;
     if (!ALIAS) {
-        if (p.host_off) {
-            uint32_t a = p.host_off[r], b = p.host_off[r + 1];
-            if (b < a) {
-                bad |= BAD_TOO_LARGE;
-                b = a;
-            }
-            h0 = a;
+        if (var_host) {
+            const uint32_t a = p.host_off[r], b = p.host_off[r + 1];
+            HB0 = p.host_off[r0];
+            HB1 = p.host_off[r0 + nrec];
+            rec_broken = rec_broken || b < a || a < HB0 || b > HB1;
+            hrel = a - (uint32_t)HB0;
             H = b - a;
         } else {
-            h0 = r * p.host_stride;
+            HB0 = r0 * p.host_stride;
+            HB1 = HB0 + (uint64_t)nrec * p.host_stride;
+            hrel = tl * p.host_stride;
             H = p.host_stride;
         }
-        if (!live)
-            H = 0;
     }
-
-    /* tile extents in the packed input streams */
-    const uint64_t D0 = p.domain_off[r0], D1 = p.domain_off[r0 + nrec];
-    uint64_t HB0 = 0, HB1 = 0;
-    if (!ALIAS) {
-        HB0 = p.host_off ? (uint64_t)p.host_off[r0] : r0 * p.host_stride;
-        HB1 = p.host_off ? (uint64_t)p.host_off[r0 + nrec] : (r0 + nrec) * p.host_stride;
-    }
-    const uint64_t dom_a0 = D0 & ~15ull, host_a0 = HB0 & ~15ull;
-    const bool fits = !p.force_generic && D1 >= D0 && HB1 >= HB0 && (D1 - dom_a0) <= p.dom_cap &&
-        (ALIAS || (HB1 - host_a0) <= p.host_cap) &&
-        ((D1 - D0) + (HB1 - HB0) + 2ull * nrec + 16) <= p.out_cap;
+    const uint32_t L = live ? d1 - d0 : 0u;
+    if (!live)
+        H = 0;
+    const uint32_t dom_span = D1 - D0, host_span = (uint32_t)(HB1 - HB0);
+    const uint32_t dom_lead = D0 & 15u, host_lead = (uint32_t)HB0 & 15u;       /* bytes staged in front of the tile's own */
 
     /* side job, part 1: issue the payload-metadata loads now so they overlap the staging below */
     const bool side = jp.n != 0;
@@ -447,30 +477,36 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
     }
 
     /* offsets that are not monotonic or point outside the buffers: refuse the tile (memory safety) */
-    {
-        bool rec_broken = live && (p.domain_off[r + 1] < d0 || d0 < D0 || d1 > D1);
-        if (!ALIAS && p.host_off && live)
-            rec_broken = rec_broken || p.host_off[r + 1] < p.host_off[r] || h0 < HB0 || h0 + H > HB1;
-        const bool tile_broken = D1 < D0 || D1 > p.dom_limit || (!ALIAS && (HB1 < HB0 || HB1 > p.host_limit));
-        if (__syncthreads_or(rec_broken || tile_broken)) {
-            if (live && (rec_broken || tile_broken))
-                report_bad(p.status, BAD_TOO_LARGE, p.rec0 + r);
-            if (side)
-                payload_length_side_job(jp, jm, jtf, live, tile);
-            return;
-        }
+    const bool tile_broken = D1 < D0 || D1 > p.dom_limit || (!ALIAS && (HB1 < HB0 || HB1 > p.host_limit));
+    if (__syncthreads_or((live && rec_broken) || tile_broken)) {            /* also publishes the mbarrier init */
+        if (live && (rec_broken || tile_broken))
+            report_bad(p.status, BAD_TOO_LARGE, p.rec0 + r);
+        if (side)
+            payload_length_side_job(jp, jm, jtf, live, tile);
+        return;
+    }
+    const bool fits = !p.force_generic && dom_lead + dom_span <= p.dom_cap &&
+        (ALIAS || host_lead + host_span <= p.host_cap) && dom_span + host_span + 2u * nrec + 16u <= p.out_cap;
+    /* whole 16-byte blocks must stay inside the caller's buffers for the bulk copies */
+    const uint32_t nd = (dom_lead + dom_span + 15u) & ~15u, nh = ALIAS ? 0u : (host_lead + host_span + 15u) & ~15u;
+    const bool bulk = fits && (uint64_t)(D0 & ~15u) + nd <= p.dom_limit && (ALIAS || (HB0 & ~15ull) + nh <= p.host_limit);
+    if (bulk && t == 0) {
+        mbar_expect_tx(&s_bar, nd + nh);
+        if (nd)
+            bulk_g2s(s_dom, p.domain_bytes + (D0 & ~15u), nd, &s_bar);
+        if (nh)
+            bulk_g2s(s_host, p.host_bytes + (HB0 & ~15ull), nh, &s_bar);
     }
 
     /* where the tile and the record go.  Closed form: slot = L + 2 + H bytes (alias: L + 1). */
     unsigned long long tile_base;
     uint32_t tile_total = 0, local = 0, slot = 0;
+    const uint32_t per_rec = ALIAS ? 1u : 2u;                   /* '/' per record, plus '/' before the hostname */
     if (!exact) {
-        const unsigned long long cf0 = (unsigned long long)D0 + (ALIAS ? r0 : HB0 + 2ull * r0);
-        const unsigned long long cf1 = (unsigned long long)D1 + (ALIAS ? r0 + nrec : HB1 + 2ull * (r0 + nrec));
-        tile_base = cf0 + p.off_bias;
-        tile_total = (uint32_t)(cf1 - cf0);
-        local = (uint32_t)(((unsigned long long)d0 + (ALIAS ? r : h0 + 2ull * r)) - cf0);
-        slot = ALIAS ? L + 1u : L + 2u + H;
+        tile_base = (unsigned long long)D0 + HB0 + (unsigned long long)per_rec * r0 + p.off_bias;
+        tile_total = dom_span + host_span + per_rec * nrec;
+        local = (d0 - D0) + hrel + per_rec * tl;
+        slot = L + H + per_rec;
     } else {
         __shared__ unsigned long long s_exact_base;
         if (t < 32) {
@@ -482,34 +518,38 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         tile_base = s_exact_base + p.off_bias;
         tile_total = p.tile_total[tile];
     }
+    const bool room = tile_base + tile_total <= p.out_capacity;
+    uint32_t bad = 0;
 
-    uint32_t len;
     if (fits) {
-        stage_in(s_dom, p.domain_bytes, D0, D1, p.dom_limit);
+        if (bulk) {
+            mbar_wait(&s_bar, 0);
+        } else {                                                /* the stream's last blocks */
+            stage_in(s_dom, p.domain_bytes, D0, D1, p.dom_limit);
+            if (!ALIAS)
+                stage_in(s_host, p.host_bytes, HB0, HB1, p.host_limit);
+            __syncthreads();
+        }
+        /* cooperative pre-pass: lower-case, dot bitmap, '.' -> '/', fence (vectorised, no divergence) */
+        uint32_t *dom_w = reinterpret_cast<uint32_t *>(s_dom);
+        const uint32_t *bits_w = reinterpret_cast<const uint32_t *>(s_bits);
+        const uint32_t *host_w = reinterpret_cast<const uint32_t *>(s_host);
+        uint32_t suspicious = prepass_domain(dom_w, reinterpret_cast<uint16_t *>(s_bits), nd >> 4, t, TILE);
         if (!ALIAS)
-            stage_in(s_host, p.host_bytes, HB0, HB1, p.host_limit);
-        __syncthreads();
-        /* cooperative pre-pass: lower-case, dot bitmap, fence (vectorised, no divergence) */
-        uint32_t suspicious = prepass_domain(reinterpret_cast<uint32_t *>(s_dom), reinterpret_cast<uint16_t *>(s_bits),
-            (uint32_t)((D1 - dom_a0 + 15) >> 4), t, TILE);
-        if (!ALIAS)
-            suspicious |= prepass_host(reinterpret_cast<const uint32_t *>(s_host), (uint32_t)((HB1 - host_a0 + 15) >> 4),
-                t, TILE);
+            suspicious |= prepass_host(host_w, nh >> 4, t, TILE);
         suspicious = __syncthreads_or(suspicious != 0);
-        const PaddedWords dsrc{reinterpret_cast<const uint32_t *>(s_dom)};
-        const PaddedWords hsrc{reinterpret_cast<const uint32_t *>(s_host)};
-        const uint32_t doff = (uint32_t)(d0 - dom_a0);
-        const uint32_t hoff = (uint32_t)(h0 - host_a0);
-        const DomainInfo di = domain_info(reinterpret_cast<const uint32_t *>(s_bits), doff, L);
+        const uint32_t doff = dom_lead + (d0 - D0);
+        const uint32_t hoff = host_lead + hrel;
+        const DomainInfo di = domain_info(bits_w, doff, L);
         if (suspicious) {
             /* something in or next to this tile is outside the fence: find out exactly which records */
-            bad |= scan_domain(dsrc, doff, L).bad;
+            bad |= recheck_domain(s_dom, bits_w, doff, L);
             if (!ALIAS && live)
-                bad |= check_host(hsrc, hoff, H);
+                bad |= check_host(PaddedWords{host_w}, hoff, H);
         } else if (!ALIAS && live && H <= 2) {
-            bad |= check_host(hsrc, hoff, H);                   /* "", "." and ".." have no bad byte */
+            bad |= check_host(PaddedWords{host_w}, hoff, H);    /* "", "." and ".." have no bad byte */
         }
-        len = live ? path_length2(di, L, H, ALIAS) : 0;
+        const uint32_t len = live ? path_length2(di, L, H, ALIAS) : 0;
         if (exact) {
             uint32_t tot;
             local = block_scan<uint32_t>(warp_sum, len, &tot);
@@ -518,31 +558,32 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         }
         if (live)
             p.out_off[r] = tile_base + local;
-        const bool room = tile_base + tile_total <= p.out_capacity;
         if (room) {
-            const uint32_t shift = (uint32_t)(tile_base & 15ull);
             WordSink sink;
-            sink.init(reinterpret_cast<uint32_t *>(s_out), local + shift);
-            if (live)
-                emit_path2<ALIAS>(dsrc, doff, L, di, hsrc, hoff, H, sink);
+            sink.init(reinterpret_cast<uint32_t *>(s_out), local + ((uint32_t)tile_base & 15u));
+            if (live) {
+                if (!ALIAS && H >= 24u)                          /* a long hostname follows: label blocks may overshoot */
+                    emit_path2<ALIAS, true>(dom_w, bits_w, doff, L, di, host_w, hoff, H, sink);
+                else
+                    emit_path2<ALIAS, false>(dom_w, bits_w, doff, L, di, host_w, hoff, H, sink);
+            }
             __syncthreads();
             if (live)
                 sink.tail();                                    /* phase B: shared boundary words */
             fence_proxy_async();
             __syncthreads();
             flush_out(p.out_bytes, s_out, tile_base, tile_total);
-        } else if (t == 0) {
-            atomicOr(&p.status->overflow, 1u);
         }
     } else {
         /* generic path: compose straight from / to global memory */
         const GuardedWords dsrc{reinterpret_cast<const uint32_t *>(p.domain_bytes)};
-        const GuardedWords hsrc{reinterpret_cast<const uint32_t *>(p.host_bytes)};
-        DomainStats st = scan_domain(dsrc, d0, L);
+        const GuardedWords hsrc{reinterpret_cast<const uint32_t *>(p.host_bytes + (var_host ? 0 : HB0))};
+        const uint32_t hoff = var_host ? (uint32_t)HB0 + hrel : hrel;
+        const DomainStats st = scan_domain(dsrc, d0, L);
         bad |= st.bad;
         if (!ALIAS && live)
-            bad |= check_host(hsrc, (uint32_t)h0, H);
-        len = live ? path_length(st, L, H, ALIAS) : 0;
+            bad |= check_host(hsrc, hoff, H);
+        const uint32_t len = live ? path_length(st, L, H, ALIAS) : 0;
         if (exact) {
             uint32_t tot;
             local = block_scan<uint32_t>(warp_sum, len, &tot);
@@ -551,17 +592,14 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         }
         if (live)
             p.out_off[r] = tile_base + local;
-        const bool room = tile_base + tile_total <= p.out_capacity;
-        if (room) {
-            if (live) {
-                ByteSink sink;
-                sink.init(p.out_bytes + tile_base + local);
-                emit_path<ALIAS>(dsrc, d0, L, hsrc, (uint32_t)h0, H, sink);
-            }
-        } else if (t == 0) {
-            atomicOr(&p.status->overflow, 1u);
+        if (room && live) {
+            ByteSink sink;
+            sink.init(p.out_bytes + tile_base + local);
+            emit_path<ALIAS>(dsrc, d0, L, hsrc, hoff, H, sink);
         }
     }
+    if (!room && t == 0)
+        atomicOr(&p.status->overflow, 1u);
     if (live)
         report_bad(p.status, bad, p.rec0 + r);
     if (r0 + nrec == p.n && t == 0) {

@@ -80,7 +80,7 @@ uint32_t emul_paths(const regk_batch *b, int generic, uint8_t *out_bytes, uint64
                 PaddedWords ds{sdom.data()}, hs{shost.data()};
                 di[t] = domain_info(sbits.data(), (uint32_t)(d0 - da0), L);
                 if (suspicious) {
-                    bad = scan_domain(ds, (uint32_t)(d0 - da0), L).bad;
+                    bad = recheck_domain((const uint8_t *)sdom.data(), sbits.data(), (uint32_t)(d0 - da0), L);
                     if (!alias)
                         bad |= check_host(hs, (uint32_t)(h0 - ha0), H);
                 } else if (!alias && H <= 2) {
@@ -119,10 +119,13 @@ uint32_t emul_paths(const regk_batch *b, int generic, uint8_t *out_bytes, uint64
                 PaddedWords ds{sdom.data()}, hs{shost.data()};
                 WordSink &sink = sinks[tt];
                 sink.init(sout.data(), local[tt] + shift);
+                const uint32_t dof = (uint32_t)(d0 - da0), hof = (uint32_t)(h0 - ha0);
                 if (alias)
-                    emit_path2<true>(ds, (uint32_t)(d0 - da0), L, di[tt], hs, (uint32_t)(h0 - ha0), H, sink);
+                    emit_path2<true, false>(sdom.data(), sbits.data(), dof, L, di[tt], shost.data(), hof, H, sink);
+                else if (H >= 24)
+                    emit_path2<false, true>(sdom.data(), sbits.data(), dof, L, di[tt], shost.data(), hof, H, sink);
                 else
-                    emit_path2<false>(ds, (uint32_t)(d0 - da0), L, di[tt], hs, (uint32_t)(h0 - ha0), H, sink);
+                    emit_path2<false, false>(sdom.data(), sbits.data(), dof, L, di[tt], shost.data(), hof, H, sink);
             }
         }
         if (!generic)

@@ -7,6 +7,7 @@ from registrar_b200.batch import RecordBatch
 
 def main():
     ctx = _native.Context(0)
+    ctx.set_option('chunk_records', 0)        # whole-batch launches: per-kernel event timing
     if os.environ.get('REGK_DOMCAP'):
         ctx.set_option('dom_cap', int(os.environ['REGK_DOMCAP']))
     out = []
