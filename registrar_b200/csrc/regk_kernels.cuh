@@ -417,12 +417,25 @@ __device__ __forceinline__ void payload_length_side_job(const JsonParams &jp, co
  *    jp.super_total, from which every CTA of regk_json_kernel derives its base — no separate pass over the
  *    payload metadata and no scan launch.
  */
+/* CTA-uniform facts about a tile, worked out once by thread 0 and read by everybody after one barrier */
+struct TilePlan {
+    unsigned long long tile_base;       /* where the tile's output starts in the packed stream */
+    unsigned long long HB0;             /* start of the tile's hostnames in host_bytes */
+    uint32_t D0, D1, HA1;               /* tile extents (HA1: end of the hostnames, variable-length case) */
+    uint32_t nd, nh;                    /* bytes staged for domains / hostnames (multiples of 16) */
+    uint32_t host_span;                 /* bytes of this tile's hostnames */
+    uint32_t tile_total;
+    uint32_t flags;                     /* PLAN_* */
+};
+enum : uint32_t { PLAN_BROKEN = 1, PLAN_FITS = 2, PLAN_BULK = 4, PLAN_ROOM = 8 };
+
 template <bool ALIAS>
 __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const PathParams p, const JsonParams jp)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t warp_sum[WARPS];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ TilePlan s_plan;
     uint8_t *s_dom = smem;                                      /* staged domain bytes: lower-cased, '.' -> '/' */
     uint8_t *s_bits = s_dom + p.dom_cap + 32;                   /* 1 bit per staged domain byte: was '.' */
     uint8_t *s_host = s_bits + p.dom_cap / 8 + 16;
@@ -430,8 +443,6 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
 
     const uint32_t tile = blockIdx.x;
     const uint32_t t = threadIdx.x;
-    if (t == 0)
-        mbar_init(&s_bar, 1);
     const uint64_t r0 = (uint64_t)tile * TILE;
     const uint32_t nrec = (uint32_t)min((uint64_t)TILE, p.n - r0);
     const bool live = t < nrec;
@@ -439,35 +450,59 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
     const uint64_t r = r0 + tl;
     const bool exact = p.exact != 0;
     const bool var_host = !ALIAS && p.host_off != nullptr;
+    const uint32_t per_rec = ALIAS ? 1u : 2u;                   /* '/' per record, plus '/' before the hostname */
 
-    /* ---- extents: the tile's (uniform) and this record's, relative to the tile wherever possible ---- */
-    const uint32_t D0 = p.domain_off[r0], D1 = p.domain_off[r0 + nrec];
-    const uint32_t d0 = p.domain_off[r], d1 = p.domain_off[r + 1];
-    uint64_t HB0 = 0, HB1 = 0;                                  /* tile extent in host_bytes */
-    uint32_t hrel = 0, H = 0;                                   /* record: offset from HB0, length */
-    bool rec_broken = d1 < d0 || d0 < D0 || d1 > D1;
-    if (!ALIAS) {
+    /* ---- thread 0: plan the tile, start the bulk copies ---- */
+    if (t == 0) {
+        mbar_init(&s_bar, 1);
+        TilePlan q;
+        q.D0 = p.domain_off[r0];
+        q.D1 = p.domain_off[r0 + nrec];
+        unsigned long long HB1 = 0;
+        q.HB0 = 0;
+        q.HA1 = 0;
         if (var_host) {
-            const uint32_t a = p.host_off[r], b = p.host_off[r + 1];
-            HB0 = p.host_off[r0];
-            HB1 = p.host_off[r0 + nrec];
-            rec_broken = rec_broken || b < a || a < HB0 || b > HB1;
-            hrel = a - (uint32_t)HB0;
-            H = b - a;
-        } else {
-            HB0 = r0 * p.host_stride;
-            HB1 = HB0 + (uint64_t)nrec * p.host_stride;
-            hrel = tl * p.host_stride;
-            H = p.host_stride;
+            q.HB0 = p.host_off[r0];
+            q.HA1 = p.host_off[r0 + nrec];
+            HB1 = q.HA1;
+        } else if (!ALIAS) {
+            q.HB0 = r0 * p.host_stride;
+            HB1 = q.HB0 + (unsigned long long)nrec * p.host_stride;
         }
+        const bool broken = q.D1 < q.D0 || q.D1 > p.dom_limit || (!ALIAS && (HB1 < q.HB0 || HB1 > p.host_limit));
+        const uint32_t dom_span = q.D1 - q.D0, host_span = (uint32_t)(HB1 - q.HB0);
+        const uint32_t dom_lead = q.D0 & 15u, host_lead = (uint32_t)q.HB0 & 15u;
+        q.nd = (dom_lead + dom_span + 15u) & ~15u;
+        q.nh = ALIAS ? 0u : (host_lead + host_span + 15u) & ~15u;
+        const bool fits = !broken && !p.force_generic && dom_lead + dom_span <= p.dom_cap &&
+            (ALIAS || host_lead + host_span <= p.host_cap) && dom_span + host_span + 2u * nrec + 16u <= p.out_cap;
+        /* whole 16-byte blocks must stay inside the caller's buffers for the bulk copies */
+        const bool bulk = fits && (unsigned long long)(q.D0 & ~15u) + q.nd <= p.dom_limit &&
+            (ALIAS || (q.HB0 & ~15ull) + q.nh <= p.host_limit);
+        if (bulk) {
+            mbar_expect_tx(&s_bar, q.nd + q.nh);
+            if (q.nd)
+                bulk_g2s(s_dom, p.domain_bytes + (q.D0 & ~15u), q.nd, &s_bar);
+            if (q.nh)
+                bulk_g2s(s_host, p.host_bytes + (q.HB0 & ~15ull), q.nh, &s_bar);
+        }
+        /* closed-form placement: slot = L + 2 + H bytes per record (alias: L + 1) */
+        q.tile_base = (unsigned long long)q.D0 + q.HB0 + (unsigned long long)per_rec * r0 + p.off_bias;
+        q.tile_total = dom_span + host_span + per_rec * nrec;
+        q.host_span = host_span;
+        q.flags = (broken ? PLAN_BROKEN : 0u) | (fits ? PLAN_FITS : 0u) | (bulk ? PLAN_BULK : 0u);
+        if (!exact && !broken && q.tile_base + q.tile_total <= p.out_capacity)
+            q.flags |= PLAN_ROOM;
+        s_plan = q;
     }
-    const uint32_t L = live ? d1 - d0 : 0u;
-    if (!live)
-        H = 0;
-    const uint32_t dom_span = D1 - D0, host_span = (uint32_t)(HB1 - HB0);
-    const uint32_t dom_lead = D0 & 15u, host_lead = (uint32_t)HB0 & 15u;       /* bytes staged in front of the tile's own */
 
-    /* side job, part 1: issue the payload-metadata loads now so they overlap the staging below */
+    /* ---- everybody: this record's offsets; the side job's metadata loads overlap the staging ---- */
+    const uint32_t d0 = p.domain_off[r], d1 = p.domain_off[r + 1];
+    uint32_t ha = 0, hb = 0;
+    if (var_host) {
+        ha = p.host_off[r];
+        hb = p.host_off[r + 1];
+    }
     const bool side = jp.n != 0;
     JsonMeta jm;
     TypeFrag jtf;
@@ -475,59 +510,59 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         jm = json_meta(jp, r);
         jtf = reinterpret_cast<const TypeFrag *>(jp.frag_blob)[jm.tid];
     }
+    unsigned long long exact_base = 0;
+    if (exact && t < 32)
+        exact_base = tile_base_from_totals(p.tile_total, p.super_total, tile);
+    if (exact && t == 0)
+        *reinterpret_cast<unsigned long long *>(warp_sum) = exact_base;     /* read back after the barrier, before any scan */
+    __syncthreads();                                            /* plan, mbarrier init (and exact base) published */
 
-    /* offsets that are not monotonic or point outside the buffers: refuse the tile (memory safety) */
-    const bool tile_broken = D1 < D0 || D1 > p.dom_limit || (!ALIAS && (HB1 < HB0 || HB1 > p.host_limit));
-    if (__syncthreads_or((live && rec_broken) || tile_broken)) {            /* also publishes the mbarrier init */
-        if (live && (rec_broken || tile_broken))
-            report_bad(p.status, BAD_TOO_LARGE, p.rec0 + r);
-        if (side)
-            payload_length_side_job(jp, jm, jtf, live, tile);
-        return;
-    }
-    const bool fits = !p.force_generic && dom_lead + dom_span <= p.dom_cap &&
-        (ALIAS || host_lead + host_span <= p.host_cap) && dom_span + host_span + 2u * nrec + 16u <= p.out_cap;
-    /* whole 16-byte blocks must stay inside the caller's buffers for the bulk copies */
-    const uint32_t nd = (dom_lead + dom_span + 15u) & ~15u, nh = ALIAS ? 0u : (host_lead + host_span + 15u) & ~15u;
-    const bool bulk = fits && (uint64_t)(D0 & ~15u) + nd <= p.dom_limit && (ALIAS || (HB0 & ~15ull) + nh <= p.host_limit);
-    if (bulk && t == 0) {
-        mbar_expect_tx(&s_bar, nd + nh);
-        if (nd)
-            bulk_g2s(s_dom, p.domain_bytes + (D0 & ~15u), nd, &s_bar);
-        if (nh)
-            bulk_g2s(s_host, p.host_bytes + (HB0 & ~15ull), nh, &s_bar);
-    }
-
-    /* where the tile and the record go.  Closed form: slot = L + 2 + H bytes (alias: L + 1). */
-    unsigned long long tile_base;
-    uint32_t tile_total = 0, local = 0, slot = 0;
-    const uint32_t per_rec = ALIAS ? 1u : 2u;                   /* '/' per record, plus '/' before the hostname */
-    if (!exact) {
-        tile_base = (unsigned long long)D0 + HB0 + (unsigned long long)per_rec * r0 + p.off_bias;
-        tile_total = dom_span + host_span + per_rec * nrec;
-        local = (d0 - D0) + hrel + per_rec * tl;
-        slot = L + H + per_rec;
-    } else {
-        __shared__ unsigned long long s_exact_base;
-        if (t < 32) {
-            const unsigned long long b = tile_base_from_totals(p.tile_total, p.super_total, tile);
-            if (t == 0)
-                s_exact_base = b;
-        }
-        __syncthreads();
-        tile_base = s_exact_base + p.off_bias;
+    const uint32_t flags = s_plan.flags;
+    const uint32_t D0 = s_plan.D0;
+    unsigned long long tile_base = s_plan.tile_base;
+    uint32_t tile_total = s_plan.tile_total;
+    bool room = flags & PLAN_ROOM;
+    if (exact) {
+        tile_base = *reinterpret_cast<const unsigned long long *>(warp_sum) + p.off_bias;
         tile_total = p.tile_total[tile];
+        room = !(flags & PLAN_BROKEN) && tile_base + tile_total <= p.out_capacity;
+        __syncthreads();                                        /* warp_sum is about to be reused by block_scan */
     }
-    const bool room = tile_base + tile_total <= p.out_capacity;
     uint32_t bad = 0;
+    /* a record whose own offsets are inconsistent is emptied and reported; the tile carries on */
+    bool rec_ok = d1 >= d0 && d0 >= D0 && d1 <= s_plan.D1;
+    uint32_t hrel, H;
+    if (ALIAS) {
+        hrel = 0;
+        H = 0;
+    } else if (var_host) {
+        rec_ok = rec_ok && hb >= ha && ha >= (uint32_t)s_plan.HB0 && hb <= s_plan.HA1;
+        hrel = ha - (uint32_t)s_plan.HB0;
+        H = hb - ha;
+    } else {
+        hrel = tl * p.host_stride;
+        H = p.host_stride;
+    }
+    uint32_t L = d1 - d0;
+    if (!live || !rec_ok) {
+        L = 0;
+        H = 0;
+    }
+    if (live && (!rec_ok || (flags & PLAN_BROKEN)))
+        bad = BAD_TOO_LARGE;
+    uint32_t local = rec_ok ? (d0 - D0) + hrel + per_rec * tl : 0u;
+    const uint32_t slot = L + H + per_rec;
 
-    if (fits) {
-        if (bulk) {
+    if (flags & PLAN_BROKEN) {
+        /* tile extents outside the buffers: nothing is read or written */
+    } else if (flags & PLAN_FITS) {
+        const uint32_t nd = s_plan.nd, nh = s_plan.nh;
+        if (flags & PLAN_BULK) {
             mbar_wait(&s_bar, 0);
         } else {                                                /* the stream's last blocks */
-            stage_in(s_dom, p.domain_bytes, D0, D1, p.dom_limit);
+            stage_in(s_dom, p.domain_bytes, D0, s_plan.D1, p.dom_limit);
             if (!ALIAS)
-                stage_in(s_host, p.host_bytes, HB0, HB1, p.host_limit);
+                stage_in(s_host, p.host_bytes, s_plan.HB0, s_plan.HB0 + s_plan.host_span, p.host_limit);
             __syncthreads();
         }
         /* cooperative pre-pass: lower-case, dot bitmap, '.' -> '/', fence (vectorised, no divergence) */
@@ -538,18 +573,18 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         if (!ALIAS)
             suspicious |= prepass_host(host_w, nh >> 4, t, TILE);
         suspicious = __syncthreads_or(suspicious != 0);
-        const uint32_t doff = dom_lead + (d0 - D0);
-        const uint32_t hoff = host_lead + hrel;
-        const DomainInfo di = domain_info(bits_w, doff, L);
+        const uint32_t doff = (D0 & 15u) + (d0 - D0);
+        const uint32_t hoff = ((uint32_t)s_plan.HB0 & 15u) + hrel;
+        const DomainInfo di = domain_info(bits_w, rec_ok ? doff : 0u, L);
         if (suspicious) {
             /* something in or next to this tile is outside the fence: find out exactly which records */
             bad |= recheck_domain(s_dom, bits_w, doff, L);
-            if (!ALIAS && live)
+            if (!ALIAS && live && rec_ok)
                 bad |= check_host(PaddedWords{host_w}, hoff, H);
-        } else if (!ALIAS && live && H <= 2) {
+        } else if (!ALIAS && live && rec_ok && H <= 2) {
             bad |= check_host(PaddedWords{host_w}, hoff, H);    /* "", "." and ".." have no bad byte */
         }
-        const uint32_t len = live ? path_length2(di, L, H, ALIAS) : 0;
+        const uint32_t len = (live && rec_ok) ? path_length2(di, L, H, ALIAS) : 0;
         if (exact) {
             uint32_t tot;
             local = block_scan<uint32_t>(warp_sum, len, &tot);
@@ -561,7 +596,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         if (room) {
             WordSink sink;
             sink.init(reinterpret_cast<uint32_t *>(s_out), local + ((uint32_t)tile_base & 15u));
-            if (live) {
+            if (live && rec_ok) {
                 if (!ALIAS && H >= 24u)                          /* a long hostname follows: label blocks may overshoot */
                     emit_path2<ALIAS, true>(dom_w, bits_w, doff, L, di, host_w, hoff, H, sink);
                 else
@@ -576,14 +611,15 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         }
     } else {
         /* generic path: compose straight from / to global memory */
+        const unsigned long long HB0 = s_plan.HB0;
         const GuardedWords dsrc{reinterpret_cast<const uint32_t *>(p.domain_bytes)};
         const GuardedWords hsrc{reinterpret_cast<const uint32_t *>(p.host_bytes + (var_host ? 0 : HB0))};
         const uint32_t hoff = var_host ? (uint32_t)HB0 + hrel : hrel;
         const DomainStats st = scan_domain(dsrc, d0, L);
         bad |= st.bad;
-        if (!ALIAS && live)
+        if (!ALIAS && live && rec_ok)
             bad |= check_host(hsrc, hoff, H);
-        const uint32_t len = live ? path_length(st, L, H, ALIAS) : 0;
+        const uint32_t len = (live && rec_ok) ? path_length(st, L, H, ALIAS) : 0;
         if (exact) {
             uint32_t tot;
             local = block_scan<uint32_t>(warp_sum, len, &tot);
@@ -592,13 +628,13 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         }
         if (live)
             p.out_off[r] = tile_base + local;
-        if (room && live) {
+        if (room && live && rec_ok) {
             ByteSink sink;
             sink.init(p.out_bytes + tile_base + local);
             emit_path<ALIAS>(dsrc, d0, L, hsrc, hoff, H, sink);
         }
     }
-    if (!room && t == 0)
+    if (!room && !(flags & PLAN_BROKEN) && t == 0)
         atomicOr(&p.status->overflow, 1u);
     if (live)
         report_bad(p.status, bad, p.rec0 + r);
@@ -607,7 +643,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         p.status->path_total = tile_base + tile_total;
     }
     if (side)
-        payload_length_side_job(jp, jm, jtf, live, tile);      /* part 2 */
+        payload_length_side_job(jp, jm, jtf, live, tile);
 }
 
 /* ============================================================= payloads == */
