@@ -673,34 +673,50 @@ __global__ void __launch_bounds__(TILE) regk_json_len_kernel(const JsonParams p,
     }
 }
 
+/* CTA-uniform facts of a payload tile, worked out by warp 0 */
+struct JsonPlan {
+    unsigned long long tile_base;
+    uint32_t tile_total;
+    uint32_t flags;                     /* PLAN_ROOM | PLAN_FITS */
+};
+
 __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const JsonParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint32_t warp_sum[WARPS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ JsonPlan s_plan;
     uint8_t *s_blob = smem;
     uint8_t *s_out = smem + p.blob_bytes;
 
     const uint32_t t = threadIdx.x;
-    /* fragment table -> shared memory (a few hundred bytes) */
-    for (uint32_t c = 16u * t; c < p.blob_bytes; c += 16u * TILE)
-        *reinterpret_cast<uint4 *>(s_blob + c) = *reinterpret_cast<const uint4 *>(p.frag_blob + c);
-
     const uint32_t tile = blockIdx.x;
     const uint64_t r0 = (uint64_t)tile * TILE;
     const uint32_t nrec = (uint32_t)min((uint64_t)TILE, p.n - r0);
     const bool live = t < nrec;
     const uint64_t r = r0 + (live ? t : 0);
 
+    /* warp 0: fragment table by one bulk copy (TMA), this tile's base from the two-level totals */
+    if (t < 32) {
+        if (t == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, p.blob_bytes);
+            bulk_g2s(s_blob, p.frag_blob, p.blob_bytes, &s_bar);
+        }
+        const unsigned long long b = tile_base_from_totals(p.tile_total, p.super_total, tile) + (p.base_in ? *p.base_in : 0ull);
+        if (t == 0) {
+            JsonPlan q;
+            q.tile_base = b;
+            q.tile_total = p.tile_total[tile];
+            q.flags = (b + q.tile_total <= p.out_capacity ? PLAN_ROOM : 0u) |
+                (!p.force_generic && q.tile_total + 16u <= p.out_cap ? PLAN_FITS : 0u);
+            s_plan = q;
+        }
+    }
+
     const JsonMeta m = json_meta(p, r);
     uint32_t bad = m.bad;
     const uint32_t a0 = m.a0, al = m.al, k = m.k;
-    __shared__ unsigned long long s_base;
-    if (t < 32) {                                               /* warp 0: this tile's base from the two-level totals */
-        const unsigned long long b = tile_base_from_totals(p.tile_total, p.super_total, tile);
-        if (t == 0)
-            s_base = b + (p.base_in ? *p.base_in : 0ull);
-    }
-    const uint32_t tile_total = p.tile_total[tile];
 
     /* first 16 address bytes -> registers, fenced */
     const GuardedWords asrc{reinterpret_cast<const uint32_t *>(p.addr_bytes)};
@@ -729,8 +745,11 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const J
                 bad |= BAD_ADDR_BYTE;
         }
     }
-    __syncthreads();                                            /* fragment table and s_base are visible */
-    const unsigned long long tile_base = s_base;
+    __syncthreads();                                            /* plan and mbarrier init are visible */
+    mbar_wait(&s_bar, 0);                                       /* fragment table has landed */
+    const unsigned long long tile_base = s_plan.tile_base;
+    const uint32_t tile_total = s_plan.tile_total;
+    const uint32_t flags = s_plan.flags;
     const TypeFrag tf = reinterpret_cast<const TypeFrag *>(s_blob)[m.tid];
     const uint32_t len = live ? json_meta_len(p, m, tf) : 0;
     uint32_t tot;
@@ -741,15 +760,12 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const J
     const PaddedWords blob{reinterpret_cast<const uint32_t *>(s_blob)};
     const uint32_t *ports = p.ports + m.p0;
     auto port = [ports](uint32_t i) { return ports[i]; };
-    const bool room = tile_base + tile_total <= p.out_capacity;
-    const bool fits = !p.force_generic && tile_total + 16u <= p.out_cap;
-    if (!room) {
+    if (!(flags & PLAN_ROOM)) {
         if (t == 0)
             atomicOr(&p.status->overflow, 1u);
-    } else if (fits) {
-        const uint32_t shift = (uint32_t)(tile_base & 15ull);
+    } else if (flags & PLAN_FITS) {
         WordSink sink;
-        sink.init(reinterpret_cast<uint32_t *>(s_out), local + shift);
+        sink.init(reinterpret_cast<uint32_t *>(s_out), local + ((uint32_t)tile_base & 15u));
         if (live)
             emit_json(blob, tf, aw, asrc, a0, al, m.has_ttl, m.ttl, m.has_ports, k, port, sink);
         __syncthreads();
