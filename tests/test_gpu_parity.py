@@ -288,3 +288,44 @@ def test_pipelined_errors_carry_global_record_indices(small_chunks):
         small_chunks.register_batch(RecordBatch.from_records(recs))
     assert ei.value.result.first_bad == 2100
     assert ei.value.result.bad_bits == (BAD_ADDR_BYTE | BAD_DOMAIN_BYTE)
+
+
+# ---- BASELINE.json full sizes (configs[2] 10M records; the per-GPU share of configs[4] 100M/8) ---------------
+
+def _chunked_compare(ctx, config, n, chunk, start=0):
+    """bit-exact against the oracle, chunk by chunk (bounds host memory), plus stream-level invariants"""
+    import zlib
+    p_total = j_total = 0
+    crc_p = crc_j = 0
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        batch = synth.generate(config, n=m, start=start + lo)
+        got = ctx.register_batch(batch, copy=False)
+        want = oracle.register_batch(batch)
+        assert want.bad_bits == 0
+        assert np.array_equal(got.path_off, want.path_off) and np.array_equal(got.json_off, want.json_off)
+        assert np.array_equal(got.path_bytes, want.path_bytes), "paths differ in chunk at %d" % lo
+        assert np.array_equal(got.json_bytes, want.json_bytes), "payloads differ in chunk at %d" % lo
+        # invariants that do not need the oracle: closed-form path size, monotone offsets
+        assert int(got.path_off[-1]) == int(batch.domain_off[-1]) + m * (36 + 2)
+        assert np.all(np.diff(got.json_off.astype(np.int64)) >= 42)
+        p_total += int(got.path_off[-1])
+        j_total += int(got.json_off[-1])
+        crc_p = zlib.crc32(got.path_bytes.tobytes(), crc_p)
+        crc_j = zlib.crc32(got.json_bytes.tobytes(), crc_j)
+    return p_total, j_total, crc_p, crc_j
+
+
+@pytest.mark.slow
+def test_config3_full_size_10M(ctx):
+    # BASELINE.json configs[2]: 10M records, mixed 2-6 label depth with ports[] in the payload, single B200
+    a = _chunked_compare(ctx, "config3", 10_000_000, 2_500_000)
+    # sharding invariance (configs[3]: the same stream cut differently gives the same bytes)
+    b = _chunked_compare(ctx, "config3", 10_000_000, 1_250_000)
+    assert a == b
+
+
+@pytest.mark.slow
+def test_config5_per_gpu_share_12_5M(ctx):
+    # BASELINE.json configs[4]: 100M records over 8 GPUs -> 12.5M per GPU, Zipf label lengths 1..63; rank 5's share
+    _chunked_compare(ctx, "config5", 12_500_000, 2_500_000, start=5 * 12_500_000)
