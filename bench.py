@@ -248,6 +248,33 @@ def run_b200(args):
     sampler.active.clear()
     barrier()
 
+    # ---- N > 1 only: reassemble the whole job's byte streams on every rank (BASELINE.json configs[3]) ----
+    gather = None
+    if world > 1:
+        from registrar_b200 import multigpu
+        ctx.set_option("async", 0)
+        res = ctx.register_raw(cbatches[0])
+        pb = multigpu.device_tensor(res.path_bytes, int(res.path_total), torch.uint8, dev)
+        jb = multigpu.device_tensor(res.json_bytes, int(res.json_total), torch.uint8, dev)
+        po = multigpu.device_tensor(res.path_off, n + 1, torch.int64, dev)
+        jo = multigpu.device_tensor(res.json_off, n + 1, torch.int64, dev)
+        g = multigpu.gather_streams(pb, po, jb, jo)                  # warm-up (NCCL channels, allocations)
+        barrier()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        g0.record(stream)
+        for _ in range(reps):
+            g = multigpu.gather_streams(pb, po, jb, jo)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        gms = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        gather = {"ms": float(gms[0]), "recv_bytes_per_rank": int(g.nbytes_received),
+                  "recv_GBps_per_rank": g.nbytes_received / (float(gms[0]) * 1e-3) / 1e9,
+                  "records_total": world * n,
+                  "what": "all-gather-v of path + payload byte streams and rebased offsets over NCCL (not part of `value`)"}
+
     # ---- max over ranks ----
     times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -295,6 +322,8 @@ def run_b200(args):
             "clocks": sampler.summary(),
             "impl": "b200",
         }
+        if gather:
+            line["allgather"] = gather
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(host_batches[0], args.cpu_seconds)
     if rank == 0:

@@ -48,7 +48,7 @@ namespace regk {
 #define REGK_MINB_PATH 5
 #endif
 #ifndef REGK_MINB_JSON
-#define REGK_MINB_JSON 5
+#define REGK_MINB_JSON 6
 #endif
 constexpr int TILE = REGK_TILE;                 /* records per tile == threads per CTA */
 constexpr int WARPS = TILE / 32;

@@ -1,0 +1,22 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel path once."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from registrar_b200 import _native, synth
+from registrar_b200.batch import RecordBatch
+from oracle import oracle
+
+ctx = _native.Context(0)
+def check(b, **kw):
+    got = ctx.register_batch(b, **kw); want = oracle.register_batch(b)
+    assert np.array_equal(got.path_bytes, want.path_bytes) and np.array_equal(got.json_bytes, want.json_bytes)
+for cfg in ("config2", "config3", "config5"):
+    check(synth.generate(cfg, n=3001, start=77))
+recs = [{"domain": b"a%d..b%d.c" % (i, i % 7), "hostname": b"h" * (1 + i % 40), "type": b"host",
+         "address": b"10.0.%d.%d" % (i % 200, i % 250), "ttl": [None, 30, 86400][i % 3],
+         "ports": [None, [80], [1, 65535, 443]][i % 3]} for i in range(1500)]
+check(RecordBatch.from_records(recs))                    # variable hostnames + empty labels -> exact redo
+check(RecordBatch.from_records(recs, alias=True))
+ctx.set_option("force_generic", 1); check(synth.generate("config3", n=1000)); ctx.set_option("force_generic", 0)
+ctx.set_option("chunk_records", 512); check(synth.generate("config3", n=3000)); ctx.set_option("chunk_records", 262144)
+print("sanitize_run ok")
