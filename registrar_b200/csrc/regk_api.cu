@@ -747,7 +747,7 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             host_cap = (uint32_t)std::min<uint64_t>(align16((pp.host_off ? mean_host_tile * 3 / 2 + 512 : mean_host_tile) + 16), 49152);
         }
         const uint32_t out_cap = (uint32_t)align16((uint64_t)dom_cap + host_cap + 2 * TILE + 32);
-        path_smem = (size_t)dom_cap + 32 + dom_cap / 8 + 16 + (alias ? 0 : host_cap + 32) + out_cap + 32;
+        path_smem = 16 + (size_t)dom_cap + 32 + dom_cap / 8 + 16 + (alias ? 0 : host_cap + 32) + out_cap + 32;
         if (path_smem > (size_t)ctx->max_smem_optin)
             return fail(ctx, REGK_ERR_INVALID_ARG, "path kernel needs %zu B of shared memory (> %d)", path_smem, ctx->max_smem_optin);
         pp.dom_cap = dom_cap;

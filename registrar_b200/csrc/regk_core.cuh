@@ -33,6 +33,15 @@
 
 namespace regk {
 
+/* 16-byte vector: one LDS.128 / STS.128 per thread on the GPU (consecutive threads -> conflict-free) */
+#if defined(__CUDACC__)
+typedef uint4 Quad;
+#else
+struct alignas(16) Quad {
+    uint32_t x, y, z, w;
+};
+#endif
+
 /* validation bits: keep in sync with include/regk.h */
 enum : uint32_t {
     BAD_DOMAIN_BYTE = 1u << 0,
@@ -434,19 +443,28 @@ RG_HD uint32_t movemask4(uint32_t m)
 RG_HD uint32_t prepass_domain(uint32_t *dom_words, uint16_t *bits, uint32_t nchunks, uint32_t t, uint32_t nt)
 {
     uint32_t hib = 0, slash = 0;
+    Quad *q = reinterpret_cast<Quad *>(dom_words);
     for (uint32_t c = t; c < nchunks; c += nt) {
+        const Quad in = q[c];                               /* one 128-bit shared-memory access per thread */
+        uint32_t wv[4] = {in.x, in.y, in.z, in.w};
         uint32_t m = 0;
         #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t w = dom_words[4 * c + j];
+            const uint32_t w = wv[j];
             const uint32_t v7 = w & 0x7F7F7F7Fu;
             const uint32_t x = v7 ^ 0x2E2E2E2Eu;                /* '.' -> 0x00, '/' -> 0x01 */
             const uint32_t dot = zero7(x);
             slash |= dot ^ zero7(x & 0x7E7E7E7Eu);
             hib |= w;
-            dom_words[4 * c + j] = lower7(v7) | (w & 0x80808080u) | (dot >> 7);    /* 0x2e | 1 = 0x2f */
+            wv[j] = lower7(v7) | (w & 0x80808080u) | (dot >> 7);    /* 0x2e | 1 = 0x2f */
             m |= movemask4(dot) << (4 * j);
         }
+        Quad out;
+        out.x = wv[0];
+        out.y = wv[1];
+        out.z = wv[2];
+        out.w = wv[3];
+        q[c] = out;
         bits[c] = (uint16_t)m;
     }
     return (hib & 0x80808080u) | slash;
@@ -457,10 +475,13 @@ RG_HD uint32_t prepass_domain(uint32_t *dom_words, uint16_t *bits, uint32_t nchu
 RG_HD uint32_t prepass_host(const uint32_t *host_words, uint32_t nchunks, uint32_t t, uint32_t nt)
 {
     uint32_t acc = 0;
+    const Quad *q = reinterpret_cast<const Quad *>(host_words);
     for (uint32_t c = t; c < nchunks; c += nt) {
+        const Quad in = q[c];                               /* one 128-bit shared-memory access per thread */
+        const uint32_t wv[4] = {in.x, in.y, in.z, in.w};
         #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t w = host_words[4 * c + j];
+            const uint32_t w = wv[j];
             const uint32_t x = w ^ 0x2F2F2F2Fu;
             acc |= w | ((w - 0x01010101u) & ~w) | ((x - 0x01010101u) & ~x);
         }
@@ -623,10 +644,12 @@ RG_HD uint32_t label_start_below(const uint32_t *bits, uint32_t b0, uint32_t e)
 
 /*
  * Emit one znode path from pre-passed shared-memory inputs (see emit_path for the semantics).
- * `dom` holds lower-cased bytes with every '.' already rewritten to '/', so a label that does not start
- * the domain is copied together with the separator in front of it ('/' + label in one block copy); only
- * the label at offset 0 and the hostname need an explicit '/'.  Label boundaries come from the dot bitmap
- * (one clz per label for domains up to 64 bytes, a backward word scan of the bitmap beyond that).
+ * `dom` holds lower-cased bytes with every '.' already rewritten to '/', and is readable from 16 bytes
+ * BEFORE its nominal start (`doff` is relative to dom, the caller passes dom = staged buffer + 16 bytes).
+ * Every label is copied together with the byte in front of it — the separator, already a '/'; for the
+ * label at offset 0 that byte belongs to someone else and is patched to '/' in the register block — so the
+ * label loop has no special cases.  Label boundaries come from the dot bitmap: for domains up to 64 bytes
+ * the highest remaining dot is one clz away and is cleared after use; longer domains scan bitmap words.
  * FAST: a hostname of >= 24 bytes follows the labels, so label blocks may overshoot (put_block16).
  */
 template <bool ALIAS, bool FAST>
@@ -634,22 +657,34 @@ RG_HD void emit_path2(const uint32_t *dom, const uint32_t *bits, uint32_t doff, 
     const uint32_t *host, uint32_t hoff, uint32_t H, WordSink &sink)
 {
     uint32_t e = L;                                         /* end (exclusive) of the current label, relative */
+    uint64_t dots = di.dots;
     for (;;) {
         uint32_t s;
-        if (di.small) {
-            const uint64_t below = e >= 64u ? di.dots : (di.dots & ((1ull << e) - 1ull));
-            s = 64u - clz64(below);                         /* position after the last '.' below e, or 0 */
-        } else {
+        if (di.small)
+            s = 64u - clz64(dots);                          /* position after the highest remaining '.', or 0 */
+        else
             s = label_start_below(bits, doff, e);
-        }
         if (ALIAS || e > s) {
-            const uint32_t lead = s > 0 ? 1u : 0u;          /* the separator in front of the label comes along */
-            if (!lead)
-                sink.put1('/');
-            copy_blocks<FAST>(dom, doff + s - lead, e - s + lead, sink);
+            /* bytes [s-1, e): separator + label, in 16-byte register blocks */
+            uint32_t off = doff + s - 1u, len = e - s + 1u;
+            uint32_t a[4];
+            load16(dom - 4, off + 16u, a);                  /* dom - 4 words = 16 bytes of front padding */
+            if (s == 0)
+                a[0] = (a[0] & 0xFFFFFF00u) | 0x2Fu;
+            for (;;) {
+                const uint32_t n = len < 16u ? len : 16u;
+                put_block16<FAST>(a, n, sink);
+                len -= n;
+                if (len == 0)
+                    break;
+                off += 16u;
+                load16(dom - 4, off + 16u, a);
+            }
         }
         if (s == 0)
             break;
+        if (di.small)
+            dots &= ~(1ull << (s - 1u));
         e = s - 1u;
     }
     if (!ALIAS) {

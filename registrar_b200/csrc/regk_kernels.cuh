@@ -436,7 +436,8 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
     __shared__ uint32_t warp_sum[WARPS];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ TilePlan s_plan;
-    uint8_t *s_dom = smem;                                      /* staged domain bytes: lower-cased, '.' -> '/' */
+    uint8_t *s_dom = smem + 16;                                 /* staged domain bytes (16 bytes of front padding):
+                                                                   lower-cased, '.' -> '/' */
     uint8_t *s_bits = s_dom + p.dom_cap + 32;                   /* 1 bit per staged domain byte: was '.' */
     uint8_t *s_host = s_bits + p.dom_cap / 8 + 16;
     uint8_t *s_out = s_host + (ALIAS ? 0 : p.host_cap + 32);

@@ -45,7 +45,10 @@ uint32_t emul_paths(const regk_batch *b, int generic, uint8_t *out_bytes, uint64
         const uint64_t HB1 = alias ? 0 : (b->host_off ? b->host_off[r0 + nrec] : (r0 + nrec) * b->host_stride);
         const uint64_t da0 = D0 & ~15ull, ha0 = HB0 & ~15ull;
         /* staged images, poisoned outside the tile's own bytes */
-        std::vector<uint32_t> sdom((D1 - da0) / 4 + 16, 0xA5A5A5A5u), shost((HB1 - ha0) / 4 + 16, 0x5A5A5A5Au);
+        /* 16 bytes of front padding in front of the staged domain bytes, like the kernel's s_dom */
+        std::vector<uint32_t> sdom_buf((D1 - da0) / 4 + 20, 0xA5A5A5A5u), shost((HB1 - ha0) / 4 + 16, 0x5A5A5A5Au);
+        uint32_t *sdom_p = sdom_buf.data() + 4;
+        struct { uint32_t *p; uint32_t *data() { return p; } } sdom{sdom_p};
         if (D1 > da0)
             memcpy(sdom.data(), b->domain_bytes + da0, D1 - da0);
         if (HB1 > ha0)
