@@ -60,8 +60,16 @@ struct regk_ctx {
     HostBuf h_path_bytes, h_path_off, h_json_bytes, h_json_off, h_running;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;          /* host pipelining (run_pipelined) */
     std::vector<cudaEvent_t> pipe_events;
-    /* workspace: DevStatus | tickets | tile status (stream-ordered reuse) */
+    /* workspace: DevStatus | two-level byte totals of both halves (stream-ordered reuse; host pipelining) */
     DevBuf work;
+    /* device-resident batches rotate through a ring of workspaces that a side stream re-zeroes (and copies
+       the status out of) after each use, so the main stream carries nothing but the two kernels */
+    static constexpr int NWORK = 4;
+    DevBuf work_ring[NWORK];
+    cudaEvent_t ws_clean[NWORK] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ws_clean_bytes[NWORK] = {0, 0, 0, 0};
+    cudaStream_t s_side = nullptr;
+    uint64_t ws_seq = 0;
 
     /* in-flight batches: events + pinned status per slot.  Outputs are single-buffered: with the
        "async" option several batches may be enqueued back to back (benchmark loops), each one
@@ -73,6 +81,7 @@ struct regk_ctx {
         bool path_alias = false, did_path = false;
         DevStatus *d_status = nullptr;
         DevStatus *h_status = nullptr;          /* pinned */
+        int ring = -1;                          /* workspace ring entry used by this batch */
         bool in_use = false;
         uint64_t n = 0;
         uint32_t flags = 0;
@@ -446,6 +455,14 @@ void regk_destroy(regk_ctx *ctx)
             cudaFree(b->p);
     for (cudaEvent_t e : ctx->pipe_events)
         cudaEventDestroy(e);
+    for (auto &e : ctx->ws_clean)
+        if (e)
+            cudaEventDestroy(e);
+    for (auto &wb : ctx->work_ring)
+        if (wb.p)
+            cudaFree(wb.p);
+    if (ctx->s_side)
+        cudaStreamDestroy(ctx->s_side);
     if (ctx->s_h2d)
         cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h)
@@ -702,10 +719,31 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     const size_t totals_j_off = super_p_off + nchunks * nsuper_chunk * 8;
     const size_t super_j_off = (totals_j_off + ntiles * 4 + 15) & ~(size_t)15;
     const size_t work_bytes = super_j_off + nchunks * nsuper_chunk * 8 + 64;
-    if ((rc = ensure_dev(ctx, ctx->work, work_bytes)))
-        return rc;
-    uint8_t *wk = (uint8_t *)ctx->work.p;
-    CK(cudaMemsetAsync(wk, 0, work_bytes, s));
+    uint8_t *wk;
+    int ring = -1;
+    if (pipelined) {
+        if ((rc = ensure_dev(ctx, ctx->work, work_bytes)))
+            return rc;
+        wk = (uint8_t *)ctx->work.p;
+        CK(cudaMemsetAsync(wk, 0, work_bytes, s));
+    } else {
+        ring = (int)(ctx->ws_seq++ % regk_ctx::NWORK);
+        if (!ctx->s_side) {
+            CK(cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking));
+            for (auto &e : ctx->ws_clean)
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const size_t cap_before = ctx->work_ring[ring].cap;
+        if ((rc = ensure_dev(ctx, ctx->work_ring[ring], work_bytes)))
+            return rc;
+        if (ctx->work_ring[ring].cap != cap_before)
+            ctx->ws_clean_bytes[ring] = 0;                  /* reallocated: contents unknown */
+        wk = (uint8_t *)ctx->work_ring[ring].p;
+        if (ctx->ws_clean_bytes[ring] >= work_bytes)
+            CK(cudaStreamWaitEvent(s, ctx->ws_clean[ring], 0));     /* zeroed by the side stream after its last use */
+        else
+            CK(cudaMemsetAsync(wk, 0, work_bytes, s));
+    }
     DevStatus *d_status = (DevStatus *)wk;
 
     if (n == 0) {
@@ -851,8 +889,20 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         CK(cudaEventRecord(slot.ev[2], s));
     }
     CK(cudaEventRecord(slot.ev[3], s));
-    CK(cudaMemcpyAsync(slot.h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
-    CK(cudaEventRecord(slot.ev[4], s));
+    if (ring >= 0) {
+        /* off the main stream: status read-back, then re-zero this workspace for its next turn */
+        CK(cudaStreamWaitEvent(ctx->s_side, slot.ev[3], 0));
+        CK(cudaMemcpyAsync(slot.h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, ctx->s_side));
+        CK(cudaEventRecord(slot.ev[4], ctx->s_side));
+        CK(cudaMemsetAsync(wk, 0, work_bytes, ctx->s_side));
+        CK(cudaEventRecord(ctx->ws_clean[ring], ctx->s_side));
+        ctx->ws_clean_bytes[ring] = work_bytes;
+        slot.ring = ring;
+    } else {
+        CK(cudaMemcpyAsync(slot.h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+        CK(cudaEventRecord(slot.ev[4], s));
+        slot.ring = -1;
+    }
 
     slot.in_use = true;
     slot.n = n;
@@ -892,6 +942,11 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
                 "batch needs the exact-offset redo but later batches are in flight; finish them in order");
         PathParams p = slot->path_params;
         const unsigned ntiles_r = (unsigned)((p.n + TILE - 1) / TILE);
+        const unsigned long long json_total_first = slot->h_status->json_total;
+        if (slot->ring >= 0) {
+            CK(cudaStreamWaitEvent(s, ctx->ws_clean[slot->ring], 0));   /* the side stream has re-zeroed it: what the redo needs */
+            ctx->ws_clean_bytes[slot->ring] = 0;                            /* ... and the redo dirties it again */
+        }
         CK(cudaMemsetAsync(&slot->d_status->needs_exact, 0, sizeof(uint32_t), s));
         /* the path totals were zeroed with the workspace and nothing has touched them yet */
         if (slot->path_alias)
@@ -909,6 +964,8 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess)
             return fail(ctx, REGK_ERR_CUDA, "exact-offset redo failed: %s", cudaGetErrorString(e));
+        if (slot->ring >= 0)
+            slot->h_status->json_total = json_total_first;  /* the payload half was not re-run */
         extra_launches = 2;
     }
     const DevStatus st = *slot->h_status;
