@@ -246,6 +246,36 @@ class Context:
         self._lib.regk_release(self._h, C.byref(res))
         return out
 
+    # -- two-deep submission of host batches: the next batch's H2D overlaps this batch's result traffic --
+    def submit(self, batch: RecordBatch, paths: bool = True, payloads: bool = True):
+        """Enqueue a host RecordBatch and return a ticket for collect().  Needs set_option("async", 1); the
+        batch's arrays must stay alive and unchanged until collect().  At most two tickets may be open."""
+        self.set_types(batch.types)
+        flags = (0 if paths else FLAG_NO_PATH) | (0 if payloads else FLAG_NO_JSON)
+        cb, keep = host_cbatch(batch, flags)
+        res = CResult()
+        rc = self._lib.regk_register_batch(self._h, C.byref(cb), C.byref(res))
+        if rc != REGK_OK:
+            self._check(rc, res)
+        return (res, cb, keep, batch)
+
+    def collect(self, ticket, copy: bool = False) -> HostResult:
+        """Wait for a submit()ted batch.  With copy=False the arrays are views of library-owned pinned memory,
+        valid until the second following submit()."""
+        res = ticket[0]
+        rc = self._lib.regk_finish(self._h, C.byref(res))
+        if rc != REGK_OK:
+            self._check(rc, res)
+        n = int(res.n)
+        cp = (lambda a: a.copy()) if copy else (lambda a: a)
+        out = HostResult(
+            n, cp(_as_np(res.path_bytes, int(res.path_total), np.uint8)), cp(_as_np(res.path_off, n + 1, np.uint64)),
+            cp(_as_np(res.json_bytes, int(res.json_total), np.uint8)), cp(_as_np(res.json_off, n + 1, np.uint64)),
+            float(res.kernel_ms), float(res.path_kernel_ms), float(res.json_kernel_ms), int(res.launches),
+            float(res.json_len_kernel_ms))
+        self._lib.regk_release(self._h, C.byref(res))
+        return out
+
     # -- raw access for device-resident callers (bench.py, multi-GPU host layer) --
     def register_raw(self, cbatch: CBatch, cres: Optional[CResult] = None) -> CResult:
         res = cres if cres is not None else CResult()

@@ -58,7 +58,18 @@ struct regk_ctx {
     /* outputs */
     DevBuf path_bytes, path_off, json_bytes, json_off;
     HostBuf h_path_bytes, h_path_off, h_json_bytes, h_json_off, h_running;
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;          /* host pipelining (run_pipelined) */
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;          /* host pipelining (run_pipelined, two-deep async) */
+    /* "async" host batches alternate between two complete sets of staging, device outputs and pinned result
+       buffers: batch k+1's H2D and kernels overlap batch k's D2H (issued when k+1 is submitted or k is
+       finished, whichever comes first - the copy sizes are only known once k's kernels are done) */
+    struct HostSet {
+        DevBuf in[11];
+        DevBuf path_bytes, path_off, json_bytes, json_off;
+        HostBuf h_path_bytes, h_path_off, h_json_bytes, h_json_off;
+        cudaEvent_t e_in = nullptr, e_out = nullptr;
+    };
+    HostSet hset[2];
+    uint64_t hseq = 0;
     std::vector<cudaEvent_t> pipe_events;
     /* workspace: DevStatus | two-level byte totals of both halves (stream-ordered reuse; host pipelining) */
     DevBuf work;
@@ -82,6 +93,8 @@ struct regk_ctx {
         DevStatus *d_status = nullptr;
         DevStatus *h_status = nullptr;          /* pinned */
         int ring = -1;                          /* workspace ring entry used by this batch */
+        int hset = -1;                          /* async host batch: which HostSet it lives in */
+        bool d2h_issued = false;
         bool in_use = false;
         uint64_t n = 0;
         uint32_t flags = 0;
@@ -380,6 +393,43 @@ static int run_pipelined(regk_ctx *ctx, const regk_batch *b, regk_result *res, c
     return REGK_OK;
 }
 
+/*
+ * D2H of an async host batch into its set's pinned result buffers, on the D2H stream.  Called once the
+ * batch's status has reached the host (its kernels are done), so the exact byte counts are known; a batch
+ * that failed the fence or still needs the exact-offset redo is left to regk_finish.
+ */
+static int issue_d2h(regk_ctx *ctx, regk_ctx::Slot &slot)
+{
+    const DevStatus st = *slot.h_status;
+    regk_ctx::HostSet &hs = ctx->hset[slot.hset];
+    if (st.bad_bits || st.overflow)
+        return REGK_OK;
+    if (st.needs_exact && slot.did_path)
+        return REGK_OK;
+    const uint64_t n = slot.n;
+    const bool do_path = !(slot.flags & REGK_NO_PATH), do_json = !(slot.flags & REGK_NO_JSON);
+    int rc;
+    if ((rc = ensure_host(ctx, hs.h_path_bytes, st.path_total + 16)) || (rc = ensure_host(ctx, hs.h_path_off, (n + 1) * 8)) ||
+        (rc = ensure_host(ctx, hs.h_json_bytes, st.json_total + 16)) || (rc = ensure_host(ctx, hs.h_json_off, (n + 1) * 8)))
+        return rc;
+    cudaStream_t sd = ctx->s_d2h;
+    if (n && do_path) {
+        CK(cudaMemcpyAsync(hs.h_path_bytes.p, hs.path_bytes.p, st.path_total, cudaMemcpyDeviceToHost, sd));
+        CK(cudaMemcpyAsync(hs.h_path_off.p, hs.path_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, sd));
+    } else {
+        memset(hs.h_path_off.p, 0, (n + 1) * 8);
+    }
+    if (n && do_json) {
+        CK(cudaMemcpyAsync(hs.h_json_bytes.p, hs.json_bytes.p, st.json_total, cudaMemcpyDeviceToHost, sd));
+        CK(cudaMemcpyAsync(hs.h_json_off.p, hs.json_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, sd));
+    } else {
+        memset(hs.h_json_off.p, 0, (n + 1) * 8);
+    }
+    CK(cudaEventRecord(hs.e_out, sd));
+    slot.d2h_issued = true;
+    return REGK_OK;
+}
+
 extern "C" {
 
 int regk_abi_version(void)
@@ -455,6 +505,25 @@ void regk_destroy(regk_ctx *ctx)
             cudaFree(b->p);
     for (cudaEvent_t e : ctx->pipe_events)
         cudaEventDestroy(e);
+    if (ctx->s_h2d)
+        cudaStreamSynchronize(ctx->s_h2d);
+    if (ctx->s_d2h)
+        cudaStreamSynchronize(ctx->s_d2h);
+    for (auto &hs : ctx->hset) {
+        for (auto &b : hs.in)
+            if (b.p)
+                cudaFree(b.p);
+        for (DevBuf *b : {&hs.path_bytes, &hs.path_off, &hs.json_bytes, &hs.json_off})
+            if (b->p)
+                cudaFree(b->p);
+        for (HostBuf *b : {&hs.h_path_bytes, &hs.h_path_off, &hs.h_json_bytes, &hs.h_json_off})
+            if (b->p)
+                cudaFreeHost(b->p);
+        if (hs.e_in)
+            cudaEventDestroy(hs.e_in);
+        if (hs.e_out)
+            cudaEventDestroy(hs.e_out);
+    }
     for (auto &e : ctx->ws_clean)
         if (e)
             cudaEventDestroy(e);
@@ -672,6 +741,25 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     const uint64_t chunk_records = (uint64_t)opt_get(ctx, "chunk_records", 262144) / TILE * TILE;
     const bool pipelined = !in_dev && !out_dev && !async && chunk_records && n >= 2 * chunk_records &&
         !opt_get(ctx, "force_generic", 0);
+    /* Host buffers in and out with the "async" option: two batches may be in flight, each in its own HostSet. */
+    regk_ctx::HostSet *hs = (!in_dev && !out_dev && async && n) ? &ctx->hset[ctx->hseq & 1] : nullptr;
+    if (hs) {
+        for (const auto &sl : ctx->slots)
+            if (sl.in_use && sl.hset == (int)(ctx->hseq & 1))
+                return fail(ctx, REGK_ERR_STATE,
+                    "regk_register_batch: at most two host batches may be in flight; call regk_finish on the older one");
+        if (!ctx->s_h2d) {
+            CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        }
+        if (!hs->e_in) {
+            CK(cudaEventCreateWithFlags(&hs->e_in, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&hs->e_out, cudaEventDisableTiming));
+        }
+    }
+    DevBuf *stage = hs ? hs->in : ctx->in;
+    DevBuf &o_path_bytes = hs ? hs->path_bytes : ctx->path_bytes, &o_path_off = hs ? hs->path_off : ctx->path_off,
+           &o_json_bytes = hs ? hs->json_bytes : ctx->json_bytes, &o_json_off = hs ? hs->json_off : ctx->json_off;
 
     /* ---- inputs on the device ---- */
     const void *src[11] = {b->domain_bytes, b->domain_off, b->host_bytes, b->host_off, b->type_id, b->addr_bytes,
@@ -690,13 +778,19 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
                 return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: device array %d is not 16-byte aligned", i);
             dev[i] = src[i];
         } else {
-            int rc = ensure_dev(ctx, ctx->in[i], sz[i] + 16);
+            int rc = ensure_dev(ctx, stage[i], sz[i] + 16);
             if (rc)
                 return rc;
             if (sz[i] && !pipelined)
-                CK(cudaMemcpyAsync(ctx->in[i].p, src[i], sz[i], cudaMemcpyHostToDevice, s));
-            dev[i] = ctx->in[i].p;
+                CK(cudaMemcpyAsync(stage[i].p, src[i], sz[i], cudaMemcpyHostToDevice, hs ? ctx->s_h2d : s));
+            dev[i] = stage[i].p;
         }
+    }
+    if (hs) {
+        /* this set's staging was last read by the kernels of the batch two submissions back, which has been
+           finished (checked above); the kernels below wait for the copies */
+        CK(cudaEventRecord(hs->e_in, ctx->s_h2d));
+        CK(cudaStreamWaitEvent(s, hs->e_in, 0));
     }
 
     /* ---- outputs (capacity = exact upper bounds) ---- */
@@ -704,8 +798,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     const uint64_t json_cap = do_json ? n * (uint64_t)(38 + 2 * ctx->max_type_q + 4 + 18 + 11) + 2 * addr_len +
         11 * ports_len + 16 : 16;
     int rc;
-    if ((rc = ensure_dev(ctx, ctx->path_bytes, path_cap)) || (rc = ensure_dev(ctx, ctx->path_off, (n + 1) * 8)) ||
-        (rc = ensure_dev(ctx, ctx->json_bytes, json_cap)) || (rc = ensure_dev(ctx, ctx->json_off, (n + 1) * 8)))
+    if ((rc = ensure_dev(ctx, o_path_bytes, path_cap)) || (rc = ensure_dev(ctx, o_path_off, (n + 1) * 8)) ||
+        (rc = ensure_dev(ctx, o_json_bytes, json_cap)) || (rc = ensure_dev(ctx, o_json_off, (n + 1) * 8)))
         return rc;
 
     /* ---- workspace: status | running payload totals per chunk | two-level byte totals of both halves ---- */
@@ -747,8 +841,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     DevStatus *d_status = (DevStatus *)wk;
 
     if (n == 0) {
-        CK(cudaMemsetAsync(ctx->path_off.p, 0, 8, s));
-        CK(cudaMemsetAsync(ctx->json_off.p, 0, 8, s));
+        CK(cudaMemsetAsync(o_path_off.p, 0, 8, s));
+        CK(cudaMemsetAsync(o_json_off.p, 0, 8, s));
     }
     const uint32_t force_generic = (uint32_t)opt_get(ctx, "force_generic", 0);
 
@@ -762,8 +856,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         pp.host_bytes = (const uint8_t *)dev[2];
         pp.host_off = (const uint32_t *)dev[3];
         pp.host_stride = b->host_stride;
-        pp.out_bytes = (uint8_t *)ctx->path_bytes.p;
-        pp.out_off = (unsigned long long *)ctx->path_off.p;
+        pp.out_bytes = (uint8_t *)o_path_bytes.p;
+        pp.out_off = (unsigned long long *)o_path_off.p;
         pp.out_capacity = path_cap;
         pp.exact = 0;                           /* closed-form offsets; see regk_finish for the exact redo */
         pp.tile_total = (uint32_t *)(wk + totals_p_off);
@@ -810,8 +904,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         jp.frag_blob = (const uint8_t *)ctx->blob_dev.p;
         jp.ntypes = (uint32_t)ctx->types.size();
         jp.blob_bytes = (uint32_t)ctx->blob_host.size();
-        jp.out_bytes = (uint8_t *)ctx->json_bytes.p;
-        jp.out_off = (unsigned long long *)ctx->json_off.p;
+        jp.out_bytes = (uint8_t *)o_json_bytes.p;
+        jp.out_off = (unsigned long long *)o_json_off.p;
         jp.out_capacity = json_cap;
         jp.tile_total = (uint32_t *)(wk + totals_j_off);
         jp.super_total = (unsigned long long *)(wk + super_j_off);
@@ -904,6 +998,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         slot.ring = -1;
     }
 
+    slot.hset = hs ? (int)(hs - ctx->hset) : -1;
+    slot.d2h_issued = false;
     slot.in_use = true;
     slot.n = n;
     slot.flags = b->flags;
@@ -914,6 +1010,19 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     res->flags = out_dev ? REGK_OUT_DEVICE : 0;
     res->launches = launches;
     res->opaque = &slot;
+    if (hs) {
+        /* the other set's batch, if still open: its kernels ran ahead of this batch's copies - start its D2H now
+           so that it overlaps this batch's H2D */
+        ctx->hseq++;
+        for (auto &sl : ctx->slots)
+            if (&sl != &slot && sl.in_use && sl.hset >= 0 && !sl.d2h_issued) {
+                cudaError_t e = cudaEventSynchronize(sl.ev[4]);
+                if (e != cudaSuccess)
+                    return fail(ctx, REGK_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
+                if ((rc = issue_d2h(ctx, sl)))
+                    return rc;
+            }
+    }
     if (async)
         return REGK_OK;
     return regk_finish(ctx, res);
@@ -937,7 +1046,7 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     if (slot->h_status->needs_exact && !slot->h_status->bad_bits && slot->did_path) {
         /* Some domain has empty labels (path.join drops them): the closed-form offsets do not hold.
            Re-run the path half with exact lengths: length kernel + last-CTA scan, then compose. */
-        if (ctx->pending)
+        if (ctx->pending && slot->hset < 0)         /* device outputs are single-buffered; host sets are not */
             return fail(ctx, REGK_ERR_STATE,
                 "batch needs the exact-offset redo but later batches are in flight; finish them in order");
         PathParams p = slot->path_params;
@@ -1002,6 +1111,20 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
         return REGK_OK;
     }
     int rc;
+    if (slot->hset >= 0) {
+        regk_ctx::HostSet &hs = ctx->hset[slot->hset];
+        if (!slot->d2h_issued && (rc = issue_d2h(ctx, *slot)))
+            return rc;
+        e = cudaEventSynchronize(hs.e_out);
+        if (e != cudaSuccess)
+            return fail(ctx, REGK_ERR_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
+        res->flags = 0;
+        res->path_bytes = (uint8_t *)hs.h_path_bytes.p;
+        res->path_off = (uint64_t *)hs.h_path_off.p;
+        res->json_bytes = (uint8_t *)hs.h_json_bytes.p;
+        res->json_off = (uint64_t *)hs.h_json_off.p;
+        return REGK_OK;
+    }
     const bool do_path = !(slot->flags & REGK_NO_PATH), do_json = !(slot->flags & REGK_NO_JSON);
     if ((rc = ensure_host(ctx, ctx->h_path_bytes, st.path_total + 16)) || (rc = ensure_host(ctx, ctx->h_path_off, (n + 1) * 8)) ||
         (rc = ensure_host(ctx, ctx->h_json_bytes, st.json_total + 16)) || (rc = ensure_host(ctx, ctx->h_json_off, (n + 1) * 8)))

@@ -235,13 +235,14 @@ def test_corrupt_offsets_are_refused_not_dereferenced(ctx):
     assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
 
 
-# ---- host pipelining (chunked H2D | kernels | D2H overlap inside regk_register_batch) -----------------
+# ---- host batches: chunked H2D | kernels | D2H overlap inside one call; two batches in flight with "async" ----
 
 @pytest.fixture()
 def small_chunks(ctx):
     ctx.set_option("chunk_records", 512)
     yield ctx
     ctx.set_option("chunk_records", 262144)
+    ctx.set_option("async", 0)
 
 
 @pytest.mark.parametrize("config,n", [("config1", 1024), ("config3", 5000), ("config5", 4097), ("config2", 1536)])
@@ -250,6 +251,42 @@ def test_pipelined_chunks_equal_the_oracle(small_chunks, config, n):
     got = small_chunks.register_batch(batch)
     assert got.launches >= 2 * (n // 512)            # really went chunk by chunk
     assert_same(got, oracle.register_batch(batch))
+
+
+def test_async_host_two_batches_in_flight(small_chunks):
+    from registrar_b200._native import RegkError
+    ctx = small_chunks
+    batches = [synth.generate(cfg, n=n, start=s) for cfg, n, s in
+               (("config2", 3000, 1), ("config3", 4100, 2), ("config5", 2500, 3), ("config2", 1024, 4))]
+    want = [oracle.register_batch(b) for b in batches]
+    ctx.set_option("async", 1)
+    t0 = ctx.submit(batches[0])
+    t1 = ctx.submit(batches[1])
+    with pytest.raises(RegkError):                   # both result sets are spoken for
+        ctx.submit(batches[2])
+    r0 = ctx.collect(t0)
+    assert_same(r0, want[0])
+    t2 = ctx.submit(batches[2])                      # reuses the first set only now
+    r1 = ctx.collect(t1)
+    assert_same(r1, want[1])                         # set 1 untouched by batch 2
+    t3 = ctx.submit(batches[3])
+    assert_same(ctx.collect(t2), want[2])
+    assert_same(ctx.collect(t3), want[3])
+    del r0
+    ctx.set_option("async", 0)
+    assert_same(ctx.register_batch(batches[0]), want[0])
+
+
+def test_async_host_batch_with_empty_labels_is_redone_at_collect(small_chunks):
+    recs = [{"domain": b"svc%d.example.com" % i, "hostname": b"h%04d" % i, "type": b"host", "address": b"10.0.0.1"}
+            for i in range(3000)]
+    recs[1234]["domain"] = b"a..b"
+    batch = RecordBatch.from_records(recs)
+    small_chunks.set_option("async", 1)
+    got = small_chunks.collect(small_chunks.submit(batch))
+    small_chunks.set_option("async", 0)
+    assert_same(got, oracle.register_batch(batch))
+    assert got.path(1234) == b"/b/a/h1234"
 
 
 def test_pipelined_variable_hostnames_alias_and_halves(small_chunks):
