@@ -42,13 +42,13 @@
 namespace regk {
 
 #ifndef REGK_TILE
-#define REGK_TILE 256
+#define REGK_TILE 128
 #endif
 #ifndef REGK_MINB_PATH
-#define REGK_MINB_PATH 5
+#define REGK_MINB_PATH 12
 #endif
 #ifndef REGK_MINB_JSON
-#define REGK_MINB_JSON 6
+#define REGK_MINB_JSON 12
 #endif
 constexpr int TILE = REGK_TILE;                 /* records per tile == threads per CTA */
 constexpr int WARPS = TILE / 32;

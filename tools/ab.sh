@@ -1,6 +1,7 @@
-for v in "" registrar_b200/ab/t128.so registrar_b200/ab/t128b.so registrar_b200/ab/t512.so registrar_b200/ab/p6.so; do
-  echo "== ${v:-base}"
-  REGK_LIB=$v timeout 300 python tools/quick_time.py 2>&1 | python -c "
+# usage: tools/ab.sh "ENV=val ..." ...   one quick_time run per argument (empty string = defaults)
+for v in "$@"; do
+  echo "== ${v:-defaults}"
+  env $v timeout 300 python tools/quick_time.py 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
