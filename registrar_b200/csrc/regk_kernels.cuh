@@ -138,7 +138,7 @@ __device__ __forceinline__ void stage_in(uint8_t *smem, const uint8_t *src, uint
  * [gbase, gbase + total).  The 16-byte-aligned body goes out as ONE bulk
  * asynchronous copy (cp.async.bulk shared::cta -> global, the TMA engine; SASS
  * UBLKCP) issued by a single thread; the < 16-byte head and tail are stored
- * byte-wise by 32 threads.  Callers must have executed fence_proxy_async() after
+ * byte-wise by the first 48 threads.  Callers must have executed fence_proxy_async() after
  * their shared-memory writes and a block barrier before calling.
  */
 __device__ __forceinline__ void fence_proxy_async()
@@ -161,12 +161,12 @@ __device__ __forceinline__ void flush_out(uint8_t *gout, const uint8_t *smem, ui
                      ::"l"(gout + a0 + body_lo), "r"(src), "r"(body_hi - body_lo) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if (t >= 32 && t < 48) {
-        const uint32_t i = lo + (t - 32);
+    if (t < 32) {                               /* head: < 16 bytes, or all of a span with no aligned block (< 31) */
+        const uint32_t i = lo + t;
         if (i < body_lo)
             gout[a0 + i] = smem[i];
-    } else if (t >= 64 && t < 80) {
-        const uint32_t i = body_hi + (t - 64);
+    } else if (t < 48) {                        /* tail: < 16 bytes */
+        const uint32_t i = body_hi + (t - 32);
         if (i < hi)
             gout[a0 + i] = smem[i];
     }

@@ -235,6 +235,26 @@ def test_corrupt_offsets_are_refused_not_dereferenced(ctx):
     assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
 
 
+def test_short_last_tile_at_every_output_phase(ctx):
+    """A last tile holding one short record (17..30 path bytes, no aligned 16-byte block inside) at every
+    byte phase of the output stream, for tile sizes 64/128/256: only head/tail byte stores, no bulk body."""
+    for tile in (64, 128, 256):
+        for pad in range(16):
+            recs = [{"domain": b"ab.cd", "hostname": b"h" * 9, "type": b"host", "address": b"10.0.0.1"}
+                    for _ in range(tile - 1)]
+            recs.append({"domain": b"ab.cd", "hostname": b"h" * (9 + pad), "type": b"host", "address": b"10.0.0.1"})
+            recs.append({"domain": b"ab.cd", "hostname": b"x" * 13, "type": b"host", "address": b"10.0.0.1"})
+            batch = RecordBatch.from_records(recs)
+            got = ctx.register_batch(batch)
+            assert got.path(tile) == b"/cd/ab/" + b"x" * 13, (tile, pad)
+            assert_same(got, oracle.register_batch(batch))
+            alias = RecordBatch.from_records(
+                [{"domain": b"a" * (14 if i < tile - 1 else 14 + pad) + b".b", "hostname": b"h", "type": b"host",
+                  "address": b"10.0.0.1"} for i in range(tile)] +
+                [{"domain": b"abcdefghijklmnopq.rs", "hostname": b"h", "type": b"host", "address": b"10.0.0.1"}], alias=True)
+            assert_same(ctx.register_batch(alias), oracle.register_batch(alias))
+
+
 # ---- host batches: chunked H2D | kernels | D2H overlap inside one call; two batches in flight with "async" ----
 
 @pytest.fixture()
