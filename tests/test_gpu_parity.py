@@ -255,6 +255,65 @@ def test_short_last_tile_at_every_output_phase(ctx):
             assert_same(ctx.register_batch(alias), oracle.register_batch(alias))
 
 
+def _random_records(rng, n, shape):
+    """in-domain records of a given 'shape': short/long labels, empty labels, short or long hostnames/addresses"""
+    alphabet = b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789-_"
+    def word(lo, hi):
+        k = int(rng.integers(lo, hi + 1))
+        return bytes(alphabet[int(c)] for c in rng.integers(0, len(alphabet), k))
+    recs = []
+    for _ in range(n):
+        depth = int(rng.integers(1, shape["depth"] + 1))
+        labels = [word(shape["lab_lo"], shape["lab_hi"]) for _ in range(depth)]
+        if shape["empty"] and rng.random() < 0.05:
+            labels[int(rng.integers(0, depth))] = b""
+        host = word(1, shape["host_hi"])
+        if host in (b".", b".."):
+            host = b"h"
+        rec = {"domain": b".".join(labels), "hostname": host, "type": [b"host", b"load_balancer", b"redis_host"][int(rng.integers(0, 3))],
+               "address": word(1, shape["addr_hi"])}
+        if rng.random() < 0.6:
+            rec["ttl"] = int(rng.choice([0, 5, 30, 86400, 2147483647, -1, -2147483648, int(rng.integers(0, 10 ** 9))]))
+        if rng.random() < 0.5:
+            rec["ports"] = [int(x) for x in rng.integers(0, 70000, int(rng.integers(0, 5)))]
+        recs.append(rec)
+    return recs
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_batches_of_every_shape(ctx, seed):
+    """Differential test against the oracle: batch sizes around the tile boundaries, label depths and lengths
+    from tiny to > 64 bytes, empty labels (exact-offset redo), long hostnames and addresses, both node kinds,
+    either half alone, shared-memory and global-memory paths."""
+    rng = np.random.default_rng(1000 + seed)
+    shapes = [dict(depth=3, lab_lo=1, lab_hi=12, host_hi=40, addr_hi=15, empty=False),
+              dict(depth=8, lab_lo=0, lab_hi=6, host_hi=5, addr_hi=4, empty=True),
+              dict(depth=4, lab_lo=20, lab_hi=70, host_hi=90, addr_hi=40, empty=False),
+              dict(depth=2, lab_lo=1, lab_hi=3, host_hi=2, addr_hi=1, empty=True)]
+    sizes = [1, 2, 31, 63, 64, 65, 127, 128, 129, 255, 256, 257, 300, 511, 513, 1000]
+    for it in range(24):
+        shape = shapes[int(rng.integers(0, len(shapes)))]
+        n = int(sizes[int(rng.integers(0, len(sizes)))])
+        recs = _random_records(rng, n, shape)
+        alias = bool(rng.random() < 0.3)
+        batch = RecordBatch.from_records(recs, alias=alias)
+        want = oracle.register_batch(batch)
+        assert want.bad_bits == 0
+        ctx.set_option("force_generic", int(rng.random() < 0.25))
+        mode = int(rng.integers(0, 4))
+        try:
+            if mode == 1:
+                got = ctx.register_batch(batch, payloads=False)
+                assert np.array_equal(got.path_bytes, want.path_bytes) and np.array_equal(got.path_off, want.path_off), (seed, it)
+            elif mode == 2:
+                got = ctx.register_batch(batch, paths=False)
+                assert np.array_equal(got.json_bytes, want.json_bytes) and np.array_equal(got.json_off, want.json_off), (seed, it)
+            else:
+                assert_same(ctx.register_batch(batch), want)
+        finally:
+            ctx.set_option("force_generic", 0)
+
+
 # ---- host batches: chunked H2D | kernels | D2H overlap inside one call; two batches in flight with "async" ----
 
 @pytest.fixture()
