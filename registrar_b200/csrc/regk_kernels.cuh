@@ -518,6 +518,11 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         *reinterpret_cast<unsigned long long *>(warp_sum) = exact_base;     /* read back after the barrier, before any scan */
     __syncthreads();                                            /* plan, mbarrier init (and exact base) published */
 
+    /* the side job runs while the bulk copies are in flight: its second-hop loads (port values) cost nothing
+       here, and its registers are free again before the composing starts */
+    if (side)
+        payload_length_side_job(jp, jm, jtf, live, tile);
+
     const uint32_t flags = s_plan.flags;
     const uint32_t D0 = s_plan.D0;
     unsigned long long tile_base = s_plan.tile_base;
@@ -643,8 +648,6 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         p.out_off[p.n] = tile_base + tile_total;
         p.status->path_total = tile_base + tile_total;
     }
-    if (side)
-        payload_length_side_job(jp, jm, jtf, live, tile);
 }
 
 /* ============================================================= payloads == */
