@@ -62,6 +62,16 @@ RG_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t shift_bits)
 #endif
 }
 
+/* left funnel shift: the high word of (hi:lo) << shift_bits, shift_bits in [0, 31] */
+RG_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t shift_bits)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, shift_bits);
+#else
+    return (uint32_t)((((((uint64_t)hi) << 32) | lo) << (shift_bits & 31)) >> 32);
+#endif
+}
+
 /* right funnel shift with the shift amount clamped to 32 (shift == 32 returns hi) */
 RG_HD uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t shift_bits)
 {
@@ -169,6 +179,17 @@ struct WordSink {
     {
         *wp++ = carry | (v << s);
         carry = funnel_rc(v, 0u, 32u - s);
+    }
+    /* N whole words in a row: one funnel shift per word instead of shift + or + carry */
+    template <int N>
+    RG_HD void put_words(const uint32_t (&v)[N])
+    {
+        wp[0] = carry | (v[0] << s);
+        #pragma unroll
+        for (int i = 1; i < N; i++)
+            wp[i] = funnel_l(v[i - 1], v[i], s);
+        carry = funnel_rc(v[N - 1], 0u, 32u - s);
+        wp += N;
     }
     /* append the low n bytes of v (1 <= n <= 4); bytes of v above n must be zero */
     RG_HD void put(uint32_t v, uint32_t n)
@@ -697,9 +718,7 @@ RG_HD void emit_path2(const uint32_t *dom, const uint32_t *bits, uint32_t doff, 
                 #pragma unroll
                 for (int i = 0; i < 9; i++)
                     h[i] = hw[i];
-                #pragma unroll
-                for (int i = 0; i < 9; i++)
-                    sink.put4(h[i]);
+                sink.put_words(h);
             } else {
                 for (uint32_t i = 0; i < nw; i++)
                     sink.put4(hw[i]);
