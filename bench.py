@@ -41,7 +41,7 @@ UNIT = "records/s"
 NB = 4                      # distinct resident batches rotated through the timed loop
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
 # workload (profiles/); None until a capture of the current kernels exists.
-NCU_TRAFFIC = {"path": 106133504, "json": 68180736}    # profiles/r1_ncu_final.txt (config2, 1M records)
+NCU_TRAFFIC = {"path": 104845824, "json": 68146944}    # profiles/r1_ncu_final.txt (config2, 1M records)
 
 
 def load_peaks():

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -182,6 +183,20 @@ size_t align16(size_t v)
     return (v + 15) & ~(size_t)15;
 }
 
+/* cudaFuncAttributeMaxDynamicSharedMemorySize is per function and device, shared by every context of the
+   process: raise it monotonically and remember the high-water mark (which: 0 alias paths, 1 node paths, 2 payloads) */
+bool smem_attr_needs_raise(int device, int which, size_t bytes)
+{
+    static std::mutex mu;
+    static size_t high[64][3];
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &h = high[device & 63][which];
+    if (bytes <= h)
+        return false;
+    h = bytes;
+    return true;
+}
+
 }  // namespace
 
 /*
@@ -317,9 +332,9 @@ static int run_pipelined(regk_ctx *ctx, const regk_batch *b, regk_result *res, c
             pp.super_total += c * hp.nsuper_chunk;
             const JsonParams side = do_json ? jp : JsonParams{};
             if (alias)
-                regk_path_kernel<true><<<(unsigned)ct, TILE, path_smem, s>>>(pp, side);
+                regk_path_kernel<true, false><<<(unsigned)ct, TILE, path_smem, s>>>(pp, side);
             else
-                regk_path_kernel<false><<<(unsigned)ct, TILE, path_smem, s>>>(pp, side);
+                regk_path_kernel<false, false><<<(unsigned)ct, TILE, path_smem, s>>>(pp, side);
             CK(cudaGetLastError());
             launches++;
         }
@@ -885,10 +900,15 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         pp.dom_cap = dom_cap;
         pp.host_cap = host_cap;
         pp.out_cap = out_cap;
-        if (alias)
-            CK(cudaFuncSetAttribute(regk_path_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
-        else
-            CK(cudaFuncSetAttribute(regk_path_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
+        if (smem_attr_needs_raise(ctx->device, alias ? 0 : 1, path_smem)) {    /* not free: only when it grows */
+            if (alias) {
+                CK(cudaFuncSetAttribute(regk_path_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
+                CK(cudaFuncSetAttribute(regk_path_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
+            } else {
+                CK(cudaFuncSetAttribute(regk_path_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
+                CK(cudaFuncSetAttribute(regk_path_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
+            }
+        }
     }
     JsonParams jp{};
     size_t json_smem = 0;
@@ -925,7 +945,9 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         json_smem = (size_t)jp.blob_bytes + out_cap + 32;
         if (json_smem > (size_t)ctx->max_smem_optin)
             return fail(ctx, REGK_ERR_INVALID_ARG, "json kernel needs %zu B of shared memory (> %d)", json_smem, ctx->max_smem_optin);
-        CK(cudaFuncSetAttribute(regk_json_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)json_smem));
+        if (smem_attr_needs_raise(ctx->device, 2, json_smem)) {
+            CK(cudaFuncSetAttribute(regk_json_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)json_smem));
+        }
     }
 
     if (pipelined) {
@@ -957,9 +979,9 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     CK(cudaEventRecord(slot.ev[0], s));
     if (n && do_path) {
         if (alias)
-            regk_path_kernel<true><<<(unsigned)ntiles, TILE, path_smem, s>>>(pp, fused_len ? jp : JsonParams{});
+            regk_path_kernel<true, false><<<(unsigned)ntiles, TILE, path_smem, s>>>(pp, fused_len ? jp : JsonParams{});
         else
-            regk_path_kernel<false><<<(unsigned)ntiles, TILE, path_smem, s>>>(pp, fused_len ? jp : JsonParams{});
+            regk_path_kernel<false, false><<<(unsigned)ntiles, TILE, path_smem, s>>>(pp, fused_len ? jp : JsonParams{});
         CK(cudaGetLastError());
         launches++;
         slot.path_params = pp;
@@ -1065,9 +1087,9 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
         CK(cudaGetLastError());
         p.exact = 1;
         if (slot->path_alias)
-            regk_path_kernel<true><<<ntiles_r, TILE, slot->path_smem, s>>>(p, JsonParams{});
+            regk_path_kernel<true, true><<<ntiles_r, TILE, slot->path_smem, s>>>(p, JsonParams{});
         else
-            regk_path_kernel<false><<<ntiles_r, TILE, slot->path_smem, s>>>(p, JsonParams{});
+            regk_path_kernel<false, true><<<ntiles_r, TILE, slot->path_smem, s>>>(p, JsonParams{});
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(slot->h_status, slot->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
         e = cudaStreamSynchronize(s);

@@ -429,7 +429,7 @@ struct TilePlan {
 };
 enum : uint32_t { PLAN_BROKEN = 1, PLAN_FITS = 2, PLAN_BULK = 4, PLAN_ROOM = 8 };
 
-template <bool ALIAS>
+template <bool ALIAS, bool EXACT>
 __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const PathParams p, const JsonParams jp)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
     const bool live = t < nrec;
     const uint32_t tl = live ? t : 0u;                          /* idle threads shadow record 0 of the tile */
     const uint64_t r = r0 + tl;
-    const bool exact = p.exact != 0;
+    constexpr bool exact = EXACT;               /* compile-time: the closed-form kernel carries none of the redo's code */
     const bool var_host = !ALIAS && p.host_off != nullptr;
     const uint32_t per_rec = ALIAS ? 1u : 2u;                   /* '/' per record, plus '/' before the hostname */
 
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         ha = p.host_off[r];
         hb = p.host_off[r + 1];
     }
-    const bool side = jp.n != 0;
+    const bool side = !EXACT && jp.n != 0;
     JsonMeta jm;
     TypeFrag jtf;
     if (side) {
