@@ -175,3 +175,51 @@ def register_batch(batch, threads: int = 0, flags_extra: int = 0, timing_only: b
 
 def max_threads() -> int:
     return int(lib().ro_max_threads())
+
+
+def usable_cpus() -> int:
+    """CPUs this process may actually run on: scheduler affinity capped by the cgroup CPU quota (a container
+    can see 128 logical CPUs and be allowed far fewer; OpenMP threads beyond that only spin)."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // period))
+        except (OSError, ValueError, IndexError):
+            pass
+    return max(1, n)
+
+
+def calibrate_threads(batch, sample: int = 500_000, seconds: float = 0.4):
+    """Thread count that gives the CPU port its best SUSTAINED throughput on this host (both bench arms use
+    it).  Candidates: the usable CPUs (affinity capped by the cgroup quota), fractions of it and the OpenMP
+    default; each runs back to back for `seconds` on a slice of the workload and is scored by its mean rate,
+    so a count that only wins until the CPU quota throttles it does not get picked.
+    Returns (threads, {threads: records/s})."""
+    sl = batch.slice(0, min(batch.n, sample))
+    cpus = usable_cpus()
+    cands = sorted({max(1, c) for c in (cpus, 2 * cpus, cpus // 2, cpus // 4, max_threads(), max_threads() // 2)})
+    rates = {}
+    for t in cands:
+        register_batch(sl, threads=t, timing_only=True)                 # thread pool of this size warmed
+        spent, reps, t_end = 0.0, 0, time.perf_counter() + seconds
+        while reps < 2 or time.perf_counter() < t_end:
+            spent += register_batch(sl, threads=t, timing_only=True).seconds
+            reps += 1
+            if spent > 4 * seconds:
+                break
+        rates[t] = sl.n * reps / spent
+    top = max(rates.values())
+    threads = min(t for t, v in rates.items() if v >= 0.93 * top)      # near-ties go to fewer threads: less
+    return threads, rates                                              # exposed to quota throttling later on
