@@ -162,7 +162,8 @@ def run_b200(args):
     n = args.records
     cfg = args.config
     ctx = _native.Context(local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)          # one explicit stream for the library's kernels, the timing events
+    torch.cuda.set_stream(stream)                   # and the NCCL calls (torch's current stream)
     ctx.set_stream(stream.cuda_stream)
 
     # ---- workload: NB distinct shards per rank, generated on the host, moved to HBM once ----
@@ -265,26 +266,41 @@ def run_b200(args):
         from registrar_b200 import multigpu
         ctx.set_option("async", 0)
         res = ctx.register_raw(cbatches[0])
+
+        def timed(fn, reps=5):
+            fn()                                                   # warm-up (channels, allocations, mappings)
+            barrier()
+            torch.cuda.synchronize()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(reps):
+                fn()
+            g1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+
+        # (a) the library's push kernel over CUDA-IPC mapped peer memory (NVLink / NVSwitch)
+        pg = multigpu.PeerGather(ctx, n, int(res.path_total), int(res.json_total), dev)
+        peer_ms = timed(lambda: pg.push(res))
+        ctx.sync()
+        recv = pg.nbytes_received()
+        # (b) the same reassembly through torch.distributed (NCCL grouped broadcasts), for comparison
         pb = multigpu.device_tensor(res.path_bytes, int(res.path_total), torch.uint8, dev)
         jb = multigpu.device_tensor(res.json_bytes, int(res.json_total), torch.uint8, dev)
         po = multigpu.device_tensor(res.path_off, n + 1, torch.int64, dev)
         jo = multigpu.device_tensor(res.json_off, n + 1, torch.int64, dev)
-        g = multigpu.gather_streams(pb, po, jb, jo)                  # warm-up (NCCL channels, allocations)
-        barrier()
-        torch.cuda.synchronize()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        g0.record(stream)
-        for _ in range(reps):
-            g = multigpu.gather_streams(pb, po, jb, jo)
-        g1.record(stream)
-        torch.cuda.synchronize()
-        gms = torch.tensor([g0.elapsed_time(g1) / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(gms[0]), "recv_bytes_per_rank": int(g.nbytes_received),
-                  "recv_GBps_per_rank": g.nbytes_received / (float(gms[0]) * 1e-3) / 1e9,
+        nccl_ms = timed(lambda: multigpu.gather_streams(pb, po, jb, jo))
+        pg.close()
+        kernels_ms = ms_total / args.steps
+        gather = {"ms": peer_ms, "recv_bytes_per_rank": recv, "recv_GBps_per_rank": recv / (peer_ms * 1e-3) / 1e9,
                   "records_total": world * n,
-                  "what": "all-gather-v of path + payload byte streams and rebased offsets over NCCL (not part of `value`)"}
+                  "records_per_s_with_gather": world * n / ((kernels_ms + peer_ms) * 1e-3),
+                  "nccl_ms": nccl_ms,
+                  "what": "all-gather-v of path + payload byte streams and rebased offsets: one push kernel over "
+                          "CUDA-IPC mapped peer memory (regk_gather_push); nccl_ms = the same through "
+                          "torch.distributed; not part of `value`"}
 
     # ---- max over ranks ----
     times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=dev)

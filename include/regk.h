@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define REGK_ABI_VERSION 1
+#define REGK_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------ */
 #define REGK_OK                 0
@@ -134,7 +134,9 @@ int         regk_create(int device, regk_ctx **out);   /* binds one CUDA device;
 void        regk_destroy(regk_ctx *ctx);
 const char *regk_last_error(const regk_ctx *ctx);      /* ctx may be NULL: error of the last failed regk_create */
 
-/* Run on a caller-supplied cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+/* Run on a caller-supplied cudaStream_t (e.g. torch's current stream); NULL = the context's own non-blocking
+ * stream.  The legacy default stream must be named explicitly (cudaStreamLegacy, (void *)0x1): a NULL here does
+ * NOT mean "stream 0", and work on the own stream is not ordered with work on the default stream. */
 int         regk_set_stream(regk_ctx *ctx, void *cuda_stream);
 
 /*
@@ -163,6 +165,43 @@ void        regk_dev_free(regk_ctx *ctx, void *p);
 int         regk_memcpy_h2d(regk_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int         regk_memcpy_d2h(regk_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 int         regk_sync(regk_ctx *ctx);
+
+/*
+ * ---- multi-GPU reassembly (BASELINE.json configs[3]: "sharded across 8 GPUs, all-gather of the output byte
+ * stream") ---------------------------------------------------------------------------------------------------
+ * One process per GPU; every rank owns whole-job result buffers (regk_dev_alloc) that its peers map through
+ * CUDA IPC.  regk_gather_push is an all-gather-v written as ONE kernel over NVLink/NVSwitch peer memory: the
+ * calling rank stores its shard's path / payload bytes at their final positions in EVERY rank's buffers
+ * (16-byte stores, re-aligned to each destination) and its record offsets rebased by the bytes of the ranks
+ * before it.  The reference has no counterpart (one registrar process per host); the operation it replaces is
+ * "concatenate the shards' results in record order" (SURVEY.md §8e).
+ */
+#define REGK_IPC_HANDLE_BYTES 64
+#define REGK_MAX_PEERS 16
+
+/* Export a device allocation made by regk_dev_alloc / map a peer's export into this process / unmap it. */
+int         regk_ipc_export(regk_ctx *ctx, const void *dev_ptr, unsigned char handle[REGK_IPC_HANDLE_BYTES]);
+int         regk_ipc_open(regk_ctx *ctx, const unsigned char handle[REGK_IPC_HANDLE_BYTES], void **peer_ptr);
+int         regk_ipc_close(regk_ctx *ctx, void *peer_ptr);
+
+typedef struct regk_gather {
+    uint32_t world, rank;
+    uint64_t rec_base;              /* records held by the ranks before this one */
+    uint64_t n_total;               /* records of the whole job */
+    const uint64_t *totals;         /* DEVICE [world][2]: {path bytes, payload bytes} of every rank's shard, as
+                                       all-gathered by the caller on the context's stream */
+    void *path_bytes[REGK_MAX_PEERS];       /* rank q's whole-job buffers as mapped in THIS process ([rank] = own) */
+    uint64_t *path_off[REGK_MAX_PEERS];     /* uint64 [n_total + 1] */
+    void *json_bytes[REGK_MAX_PEERS];
+    uint64_t *json_off[REGK_MAX_PEERS];
+    uint64_t path_cap, json_cap;    /* bytes behind every whole-job byte buffer */
+} regk_gather;
+
+/* Enqueue the push of `shard` (a finished REGK_OUT_DEVICE result of this context) on the context's stream.
+ * Remote data is complete on a rank once every rank's push has finished: follow it with a stream-ordered
+ * barrier across ranks (e.g. a 1-element NCCL all-reduce).  Out-of-range totals raise REGK_ERR_INVALID_ARG
+ * at regk_sync time through the returned device flag, never a wild store. */
+int         regk_gather_push(regk_ctx *ctx, const regk_result *shard, const regk_gather *g);
 
 /* Tuning knobs (kernel variant selection for A/B measurement); see DESIGN.md. */
 int         regk_set_option(regk_ctx *ctx, const char *name, int64_t value);

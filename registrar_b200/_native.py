@@ -60,10 +60,23 @@ class CResult(C.Structure):          # regk_result
                 ("json_len_kernel_ms", C.c_float), ("launches", C.c_uint32), ("opaque", C.c_void_p)]
 
 
+MAX_PEERS = 16
+IPC_HANDLE_BYTES = 64
+
+
+class CGather(C.Structure):          # regk_gather
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("rec_base", C.c_uint64), ("n_total", C.c_uint64),
+                ("totals", C.c_void_p),
+                ("path_bytes", C.c_void_p * MAX_PEERS), ("path_off", C.c_void_p * MAX_PEERS),
+                ("json_bytes", C.c_void_p * MAX_PEERS), ("json_off", C.c_void_p * MAX_PEERS),
+                ("path_cap", C.c_uint64), ("json_cap", C.c_uint64)]
+
+
 EXPORTS = ["regk_abi_version", "regk_create", "regk_destroy", "regk_last_error", "regk_set_stream",
            "regk_set_types", "regk_register_batch", "regk_finish", "regk_release", "regk_host_alloc",
            "regk_host_free", "regk_dev_alloc", "regk_dev_free", "regk_memcpy_h2d", "regk_memcpy_d2h",
-           "regk_sync", "regk_set_option", "regk_get_option"]
+           "regk_sync", "regk_set_option", "regk_get_option", "regk_ipc_export", "regk_ipc_open", "regk_ipc_close",
+           "regk_gather_push"]
 
 _lib = None
 
@@ -104,6 +117,10 @@ def load_library():
     lib.regk_set_option.argtypes = [vp, C.c_char_p, i64]
     lib.regk_get_option.argtypes = [vp, C.c_char_p]
     lib.regk_get_option.restype = i64
+    lib.regk_ipc_export.argtypes = [vp, vp, C.c_char_p]
+    lib.regk_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.regk_ipc_close.argtypes = [vp, vp]
+    lib.regk_gather_push.argtypes = [vp, C.POINTER(CResult), C.POINTER(CGather)]
     _lib = lib
     return lib
 
@@ -219,7 +236,14 @@ class Context:
         return int(self._lib.regk_get_option(self._h, name.encode()))
 
     def set_stream(self, cuda_stream: int):
-        self._check(self._lib.regk_set_stream(self._h, C.c_void_p(cuda_stream)))
+        """Run on the caller's CUDA stream (a cudaStream_t as an integer, e.g. torch's stream.cuda_stream).
+        torch reports the legacy default stream as 0, which the C-ABI reads as "the library's own stream":
+        0 is therefore passed on as cudaStreamLegacy (0x1), so that the caller's events, NCCL calls and the
+        library's kernels really are in one stream order.  Use set_own_stream() for the library's stream."""
+        self._check(self._lib.regk_set_stream(self._h, C.c_void_p(cuda_stream if cuda_stream else 1)))
+
+    def set_own_stream(self):
+        self._check(self._lib.regk_set_stream(self._h, None))
 
     def sync(self):
         self._check(self._lib.regk_sync(self._h))
@@ -286,6 +310,32 @@ class Context:
     def finish(self, cres: CResult) -> CResult:
         self._check(self._lib.regk_finish(self._h, C.byref(cres)), cres)
         return cres
+
+    # -- multi-GPU reassembly (regk_gather_push over CUDA-IPC mapped peer buffers) --
+    def dev_alloc(self, nbytes: int) -> int:
+        p = self._lib.regk_dev_alloc(self._h, nbytes)
+        if not p:
+            raise MemoryError("regk_dev_alloc(%d) failed" % nbytes)
+        return p
+
+    def dev_free(self, p: int):
+        self._lib.regk_dev_free(self._h, C.c_void_p(p))
+
+    def ipc_export(self, dev_ptr: int) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self._lib.regk_ipc_export(self._h, C.c_void_p(dev_ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes) -> int:
+        out = C.c_void_p()
+        self._check(self._lib.regk_ipc_open(self._h, handle, C.byref(out)))
+        return out.value
+
+    def ipc_close(self, peer_ptr: int):
+        self._lib.regk_ipc_close(self._h, C.c_void_p(peer_ptr))
+
+    def gather_push(self, shard: CResult, plan: CGather):
+        self._check(self._lib.regk_gather_push(self._h, C.byref(shard), C.byref(plan)))
 
     def host_alloc(self, nbytes: int) -> int:
         p = self._lib.regk_host_alloc(self._h, nbytes)

@@ -20,6 +20,7 @@
 
 #include "../../include/regk.h"
 #include "regk_kernels.cuh"
+#include "regk_gather.cuh"
 #include "regk_types.hpp"
 
 using namespace regk;
@@ -71,6 +72,7 @@ struct regk_ctx {
     };
     HostSet hset[2];
     uint64_t hseq = 0;
+    uint32_t *h_gather_flag = nullptr;          /* pinned: regk_gather_push found the whole-job buffers too small */
     std::vector<cudaEvent_t> pipe_events;
     /* workspace: DevStatus | two-level byte totals of both halves (stream-ordered reuse; host pipelining) */
     DevBuf work;
@@ -556,6 +558,8 @@ void regk_destroy(regk_ctx *ctx)
             cudaFreeHost(b->p);
     if (ctx->h_status_block)
         cudaFreeHost(ctx->h_status_block);
+    if (ctx->h_gather_flag)
+        cudaFreeHost(ctx->h_gather_flag);
     for (auto &sl : ctx->slots)
         for (auto &ev : sl.ev)
             if (ev)
@@ -692,6 +696,90 @@ int regk_sync(regk_ctx *ctx)
         return REGK_ERR_INVALID_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_gather_flag && *ctx->h_gather_flag) {
+        *ctx->h_gather_flag = 0;
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_gather_push: the totals table exceeds the whole-job buffers or disagrees with the shard; nothing was stored");
+    }
+    return REGK_OK;
+}
+
+int regk_ipc_export(regk_ctx *ctx, const void *dev_ptr, unsigned char handle[REGK_IPC_HANDLE_BYTES])
+{
+    if (!ctx || !dev_ptr || !handle)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_ipc_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == REGK_IPC_HANDLE_BYTES, "IPC handle size");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+    memcpy(handle, &h, sizeof h);
+    return REGK_OK;
+}
+
+int regk_ipc_open(regk_ctx *ctx, const unsigned char handle[REGK_IPC_HANDLE_BYTES], void **peer_ptr)
+{
+    if (!ctx || !handle || !peer_ptr)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_ipc_open: NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    *peer_ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return REGK_OK;
+}
+
+int regk_ipc_close(regk_ctx *ctx, void *peer_ptr)
+{
+    if (!ctx || !peer_ptr)
+        return REGK_ERR_INVALID_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaIpcCloseMemHandle(peer_ptr));
+    return REGK_OK;
+}
+
+int regk_gather_push(regk_ctx *ctx, const regk_result *shard, const regk_gather *g)
+{
+    if (!ctx || !shard || !g)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_gather_push: NULL argument");
+    if (g->world == 0 || g->world > REGK_MAX_PEERS || g->rank >= g->world)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_gather_push: world %u / rank %u out of range (at most %d peers)",
+            g->world, g->rank, REGK_MAX_PEERS);
+    if (!(shard->flags & REGK_OUT_DEVICE) || !shard->path_off || !shard->json_off)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_gather_push: the shard must be a finished REGK_OUT_DEVICE result");
+    if (!g->totals || g->rec_base + shard->n > g->n_total)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_gather_push: totals missing or record range outside the job");
+    for (uint32_t q = 0; q < g->world; q++)
+        if (!g->path_bytes[q] || !g->path_off[q] || !g->json_bytes[q] || !g->json_off[q] ||
+            (((uintptr_t)g->path_bytes[q] | (uintptr_t)g->json_bytes[q]) & 15) || (((uintptr_t)g->path_off[q] | (uintptr_t)g->json_off[q]) & 7))
+            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_gather_push: buffer of rank %u missing or misaligned", q);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->h_gather_flag) {
+        CK(cudaMallocHost((void **)&ctx->h_gather_flag, sizeof(uint32_t)));
+        *ctx->h_gather_flag = 0;
+    }
+    GatherParams p{};
+    p.world = g->world;
+    p.rank = g->rank;
+    p.n_local = shard->n;
+    p.rec_base = g->rec_base;
+    p.n_total = g->n_total;
+    p.totals = (const unsigned long long *)g->totals;
+    p.src_path = shard->path_bytes;
+    p.src_json = shard->json_bytes;
+    p.src_path_off = (const unsigned long long *)shard->path_off;
+    p.src_json_off = (const unsigned long long *)shard->json_off;
+    for (uint32_t q = 0; q < g->world; q++) {
+        p.dst_path[q] = (uint8_t *)g->path_bytes[q];
+        p.dst_json[q] = (uint8_t *)g->json_bytes[q];
+        p.dst_path_off[q] = (unsigned long long *)g->path_off[q];
+        p.dst_json_off[q] = (unsigned long long *)g->json_off[q];
+    }
+    p.path_cap = g->path_cap;
+    p.json_cap = g->json_cap;
+    p.my_path_total = shard->path_total;
+    p.my_json_total = shard->json_total;
+    p.flag = ctx->h_gather_flag;
+    regk_gather_push_kernel<<<(unsigned)ctx->sm_count * 4, 256, 0, ctx->stream>>>(p);
+    CK(cudaGetLastError());
     return REGK_OK;
 }
 

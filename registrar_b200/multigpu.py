@@ -8,7 +8,10 @@ NVLink/NVSwitch (torch.distributed / NCCL: with unequal sizes ProcessGroupNCCL i
 broadcast per rank straight into views of the final buffer, so there is no padding and no compaction
 pass).  Offsets are rebased by the exclusive scan of the totals.
 
-Works on any torch.distributed backend (NCCL on GPUs, gloo on CPU for the host-logic tests).
+`gather_streams` works on any torch.distributed backend (NCCL on GPUs, gloo on CPU for the host-logic
+tests).  On the GPUs of one box `PeerGather` is the fast path: every rank's whole-job buffers are mapped
+into its peers through CUDA IPC and one kernel of the library (regk_gather_push, include/regk.h) stores
+the shard straight into all of them over NVLink / NVSwitch, offsets rebased on the fly.
 """
 from __future__ import annotations
 
@@ -113,3 +116,89 @@ def gather_streams(path_bytes: torch.Tensor, path_off: torch.Tensor, json_bytes:
     off_j[n_total] = sum(jsz)
     recv = (sum(psz) - psz[rank]) + (sum(jsz) - jsz[rank]) + 16 * (n_total - n_local)
     return Gathered(out_p, off_p, out_j, off_j, counts, recv)
+
+
+class PeerGather:
+    """All-gather-v of the shards' results over NVLink peer memory (regk_gather_push).
+
+    One instance per rank.  Construction is collective: it sizes the whole-job buffers from the ranks'
+    capacities, allocates them with the library (cudaMalloc), exchanges CUDA IPC handles through the process
+    group and maps every peer's buffers.  `push(result)` is collective too: a 16-byte all-gather of the
+    shards' byte totals (stream-ordered, no host round trip), the library's push kernel, and a 1-element
+    all-reduce as the cross-rank barrier.  Afterwards `path_bytes / path_off / json_bytes / json_off` hold
+    the job-wide streams on every rank.
+    """
+
+    def __init__(self, ctx, n_local: int, path_cap_local: int, json_cap_local: int, device, group=None):
+        from . import _native
+        self.ctx, self.group, self.device = ctx, group, device
+        # the totals all-gather, the push kernel and the closing all-reduce must share one stream order
+        ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > _native.MAX_PEERS:
+            raise ValueError("PeerGather supports at most %d ranks" % _native.MAX_PEERS)
+        caps = [None] * self.world
+        dist.all_gather_object(caps, (int(n_local), int(path_cap_local), int(json_cap_local)), group=group)
+        self.counts = [c[0] for c in caps]
+        self.n_total = sum(self.counts)
+        self.rec_base = sum(self.counts[:self.rank])
+        self.path_cap = sum(c[1] for c in caps) + 64
+        self.json_cap = sum(c[2] for c in caps) + 64
+        sizes = (self.path_cap, (self.n_total + 1) * 8, self.json_cap, (self.n_total + 1) * 8)
+        self._own = [ctx.dev_alloc(s) for s in sizes]
+        handles = [None] * self.world
+        dist.all_gather_object(handles, [ctx.ipc_export(p) for p in self._own], group=group)
+        self._peers = []                         # [rank][4] device pointers valid in this process
+        for q in range(self.world):
+            self._peers.append(list(self._own) if q == self.rank else [ctx.ipc_open(h) for h in handles[q]])
+        plan = _native.CGather()
+        plan.world, plan.rank = self.world, self.rank
+        plan.rec_base, plan.n_total = self.rec_base, self.n_total
+        plan.path_cap, plan.json_cap = self.path_cap, self.json_cap
+        for q in range(self.world):
+            plan.path_bytes[q], plan.path_off[q], plan.json_bytes[q], plan.json_off[q] = self._peers[q]
+        self._plan = plan
+        self._totals = torch.zeros(self.world, 2, dtype=torch.int64, device=device)
+        self._mine = torch.zeros(2, dtype=torch.int64, device=device)
+        self._token = torch.zeros(1, dtype=torch.int32, device=device)
+        plan.totals = self._totals.data_ptr()
+        self.path_bytes = device_tensor(self._own[0], self.path_cap, torch.uint8, device)
+        self.path_off = device_tensor(self._own[1], self.n_total + 1, torch.int64, device)
+        self.json_bytes = device_tensor(self._own[2], self.json_cap, torch.uint8, device)
+        self.json_off = device_tensor(self._own[3], self.n_total + 1, torch.int64, device)
+        dist.barrier(group=group)
+
+    def push(self, shard) -> None:
+        """shard: the finished REGK_OUT_DEVICE CResult of this rank (its n must be the n_local given at
+        construction).  Everything is enqueued on the current stream; returns without synchronising."""
+        if int(shard.n) != self.counts[self.rank]:
+            raise ValueError("shard holds %d records, this gather was built for %d" % (int(shard.n), self.counts[self.rank]))
+        self._mine[0] = int(shard.path_total)
+        self._mine[1] = int(shard.json_total)
+        dist.all_gather_into_tensor(self._totals.view(-1), self._mine, group=self.group)
+        self.ctx.gather_push(shard, self._plan)
+        dist.all_reduce(self._token, group=self.group)          # every rank's stores have landed after this
+
+    def nbytes_received(self, totals=None) -> int:
+        t = self._totals.cpu() if totals is None else totals
+        others = [q for q in range(self.world) if q != self.rank]
+        return int(sum(int(t[q, 0]) + int(t[q, 1]) for q in others) + 16 * (self.n_total - self.counts[self.rank]))
+
+    def result(self) -> Gathered:
+        """Job-wide views (after the stream has passed the push): byte streams trimmed to their totals."""
+        t = self._totals.cpu()
+        p_total, j_total = int(t[:, 0].sum()), int(t[:, 1].sum())
+        return Gathered(self.path_bytes[:p_total], self.path_off, self.json_bytes[:j_total], self.json_off,
+                        list(self.counts), self.nbytes_received(t))
+
+    def close(self) -> None:
+        dist.barrier(group=self.group)                          # nobody unmaps while a peer may still be storing
+        for q, ptrs in enumerate(self._peers):
+            if q != self.rank:
+                for p in ptrs:
+                    self.ctx.ipc_close(p)
+        dist.barrier(group=self.group)
+        for p in self._own:
+            self.ctx.dev_free(p)
+        self._peers, self._own = [], []

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(built):
     for s in syms:
         assert hasattr(lib, s), "libregk.so does not export %s" % s
     assert sorted(_native.EXPORTS) == syms
-    assert lib.regk_abi_version() == 1
+    assert lib.regk_abi_version() == 2
 
 
 def test_no_gpu_means_failure_not_fallback(built):
@@ -48,9 +48,10 @@ def test_struct_layouts_match_header(built):
     #include <stddef.h>
     #include "regk.h"
     int main(void) {
-        printf("%zu %zu %zu %zu %zu %zu\n", sizeof(regk_batch), offsetof(regk_batch, domain_bytes),
+        printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(regk_batch), offsetof(regk_batch, domain_bytes),
                offsetof(regk_batch, ports_present), sizeof(regk_result), offsetof(regk_result, json_total),
-               offsetof(regk_result, opaque));
+               offsetof(regk_result, opaque), sizeof(regk_gather), offsetof(regk_gather, totals),
+               offsetof(regk_gather, json_off), offsetof(regk_gather, json_cap));
         return 0;
     }'''
     with tempfile.TemporaryDirectory() as d:
@@ -58,5 +59,7 @@ def test_struct_layouts_match_header(built):
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
     got = [C.sizeof(_native.CBatch), _native.CBatch.domain_bytes.offset, _native.CBatch.ports_present.offset,
-           C.sizeof(_native.CResult), _native.CResult.json_total.offset, _native.CResult.opaque.offset]
+           C.sizeof(_native.CResult), _native.CResult.json_total.offset, _native.CResult.opaque.offset,
+           C.sizeof(_native.CGather), _native.CGather.totals.offset, _native.CGather.json_off.offset,
+           _native.CGather.json_cap.offset]
     assert [int(x) for x in out] == got

@@ -1,5 +1,6 @@
 """Multi-GPU path on real GPUs (skipped with fewer than 2): two ranks (NCCL) shard a config-3 stream, run the
-kernels on their shards and all-gather-v the byte streams; the gathered stream must equal the single-GPU one."""
+kernels on their shards and all-gather-v the byte streams - once through torch.distributed, once through the
+library's own push kernel over CUDA-IPC mapped peer memory; both must equal the single-GPU stream."""
 import os
 import subprocess
 import sys
@@ -38,6 +39,20 @@ whole = oracle.register_batch(synth.generate("config3", n=N, start=0))
 ok = (np.array_equal(g.path_bytes.cpu().numpy(), whole.path_bytes) and np.array_equal(g.json_bytes.cpu().numpy(), whole.json_bytes)
       and np.array_equal(g.path_off.cpu().numpy().astype(np.uint64), whole.path_off)
       and np.array_equal(g.json_off.cpu().numpy().astype(np.uint64), whole.json_off))
+# the same reassembly as one push kernel over CUDA-IPC mapped peer buffers (regk_gather_push)
+pg = multigpu.PeerGather(ctx, n, int(res.path_total), int(res.json_total), dev)
+for _ in range(2):                                   # twice: the buffers are reused from step to step
+    pg.push(res)
+torch.cuda.synchronize()
+ctx.sync()
+g2 = pg.result()
+ok2 = (np.array_equal(g2.path_bytes.cpu().numpy(), whole.path_bytes) and np.array_equal(g2.json_bytes.cpu().numpy(), whole.json_bytes)
+       and np.array_equal(g2.path_off.cpu().numpy().astype(np.uint64), whole.path_off)
+       and np.array_equal(g2.json_off.cpu().numpy().astype(np.uint64), whole.json_off)
+       and g2.nbytes_received == g.nbytes_received)
+pg.close()
+print("RANK", rank, "PEER", "OK" if ok2 else "MISMATCH", flush=True)
+ok = ok and ok2
 print("RANK", rank, "OK" if ok else "MISMATCH", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
@@ -54,4 +69,5 @@ def test_two_rank_gather_equals_single_stream(built, tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("OK") == 2
+    assert out.stdout.count("PEER OK") == 2, out.stdout[-2000:]
+    assert out.stdout.count("OK") == 4
