@@ -41,6 +41,7 @@ UNIT = "records/s"
 NB = 4                      # distinct resident batches rotated through the timed loop
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
 # workload (profiles/); None until a capture of the current kernels exists.
+TIME_EVERY = int(os.environ.get("REGK_TIME_EVERY", "8"))
 NCU_TRAFFIC = {"path": 104845824, "json": 68146944}    # profiles/r1_ncu_final.txt (config2, 1M records)
 
 
@@ -194,16 +195,18 @@ def run_b200(args):
 
     # ---- device-resident arm: `value` ----
     ctx.set_option("async", 1)
+    ctx.set_option("time_every", TIME_EVERY)        # per-kernel CUDA events on every TIME_EVERY-th step of the timed region
     inflight = []
     stats = {"path_ms": 0.0, "json_ms": 0.0, "steps": 0, "path_total": 0, "json_total": 0, "launches": 0}
 
     def drain(limit, count):
         while len(inflight) > limit:
             r = ctx.finish(inflight.pop(0))
-            if count:
+            if count and r.kernel_ms > 0:                          # a step that carried the timing events
                 stats["path_ms"] += r.path_kernel_ms
                 stats["json_ms"] += r.json_kernel_ms
                 stats["steps"] += 1
+            if count:
                 stats["launches"] += r.launches
                 stats["path_total"], stats["json_total"] = int(r.path_total), int(r.json_total)
 
@@ -226,6 +229,7 @@ def run_b200(args):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     ctx.set_option("async", 0)
+    ctx.set_option("time_every", 1)
     if os.environ.get("REGK_CHUNK"):
         ctx.set_option("chunk_records", int(os.environ["REGK_CHUNK"]))
 
@@ -322,7 +326,9 @@ def run_b200(args):
             ach = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             return {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes": nbytes,
-                    "mean_launch_ms": round(ms, 5), "peak_source": peak_src}
+                    "mean_launch_ms": round(ms, 5), "launches_timed": stats["steps"],
+                    "timing": "CUDA events around the launch on every %d-th step of the timed region" % TIME_EVERY,
+                    "peak_source": peak_src}
 
         roofs = {"path": roof("regk_path_kernel<false>", pb, p_ms), "json": roof("regk_json_kernel", jb, j_ms)}
         for k in roofs:

@@ -98,6 +98,7 @@ struct regk_ctx {
         int ring = -1;                          /* workspace ring entry used by this batch */
         int hset = -1;                          /* async host batch: which HostSet it lives in */
         bool d2h_issued = false;
+        bool timed = true;                      /* ev[0..2] were recorded for this batch */
         bool in_use = false;
         uint64_t n = 0;
         uint32_t flags = 0;
@@ -583,7 +584,7 @@ int regk_set_option(regk_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name)
         return REGK_ERR_INVALID_ARG;
-    static const char *known[] = {"async", "force_generic", "dom_cap", "json_out_cap", "chunk_records", nullptr};
+    static const char *known[] = {"async", "force_generic", "dom_cap", "json_out_cap", "chunk_records", "time_every", nullptr};
     for (const char **k = known; *k; k++)
         if (!strcmp(*k, name)) {
             ctx->opt[name] = value;
@@ -937,7 +938,14 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             ctx->ws_clean_bytes[ring] = 0;                  /* reallocated: contents unknown */
         wk = (uint8_t *)ctx->work_ring[ring].p;
         if (ctx->ws_clean_bytes[ring] >= work_bytes)
-            CK(cudaStreamWaitEvent(s, ctx->ws_clean[ring], 0));     /* zeroed by the side stream after its last use */
+        {
+            /* zeroed by the side stream after its last use, normally long ago: only a cleaning still in
+               flight becomes a stream dependency (every extra stream operation opens a gap between kernels) */
+            if (cudaEventQuery(ctx->ws_clean[ring]) != cudaSuccess) {
+                cudaGetLastError();
+                CK(cudaStreamWaitEvent(s, ctx->ws_clean[ring], 0));
+            }
+        }
         else
             CK(cudaMemsetAsync(wk, 0, work_bytes, s));
     }
@@ -1064,7 +1072,13 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     slot.did_path = false;
     slot.d_status = d_status;
     const bool fused_len = n && do_path && do_json;
-    CK(cudaEventRecord(slot.ev[0], s));
+    /* per-kernel timing events sit between the launches and cost a few microseconds of stream gaps per batch:
+       "time_every" = K keeps them on every K-th batch only (the others report kernel times of 0) */
+    const int64_t time_every = std::max<int64_t>(1, opt_get(ctx, "time_every", 1));
+    const bool timed = ctx->seq % (uint64_t)time_every == 0;
+    slot.timed = timed;
+    if (timed)
+        CK(cudaEventRecord(slot.ev[0], s));
     if (n && do_path) {
         if (alias)
             regk_path_kernel<true, false><<<(unsigned)ntiles, TILE, path_smem, s>>>(pp, fused_len ? jp : JsonParams{});
@@ -1077,7 +1091,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         slot.path_alias = alias;
         slot.did_path = true;
     }
-    CK(cudaEventRecord(slot.ev[1], s));
+    if (timed)
+        CK(cudaEventRecord(slot.ev[1], s));
     if (n && do_json) {
         if (!fused_len) {
             const unsigned len_grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 8);
@@ -1085,11 +1100,12 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             CK(cudaGetLastError());
             launches++;
         }
-        CK(cudaEventRecord(slot.ev[2], s));
+        if (timed)
+            CK(cudaEventRecord(slot.ev[2], s));
         regk_json_kernel<<<(unsigned)ntiles, TILE, json_smem, s>>>(jp);
         CK(cudaGetLastError());
         launches++;
-    } else {
+    } else if (timed) {
         CK(cudaEventRecord(slot.ev[2], s));
     }
     CK(cudaEventRecord(slot.ev[3], s));
@@ -1191,9 +1207,11 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     const uint64_t n = slot->n;
     const bool out_dev = slot->flags & REGK_OUT_DEVICE;
     float ms_p = 0, ms_jl = 0, ms_j = 0;
-    cudaEventElapsedTime(&ms_p, slot->ev[0], slot->ev[1]);
-    cudaEventElapsedTime(&ms_jl, slot->ev[1], slot->ev[2]);
-    cudaEventElapsedTime(&ms_j, slot->ev[2], slot->ev[3]);
+    if (slot->timed) {
+        cudaEventElapsedTime(&ms_p, slot->ev[0], slot->ev[1]);
+        cudaEventElapsedTime(&ms_jl, slot->ev[1], slot->ev[2]);
+        cudaEventElapsedTime(&ms_j, slot->ev[2], slot->ev[3]);
+    }
     res->n = n;
     res->path_kernel_ms = ms_p;
     res->json_kernel_ms = ms_j;
