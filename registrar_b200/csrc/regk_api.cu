@@ -779,7 +779,7 @@ int regk_gather_push(regk_ctx *ctx, const regk_result *shard, const regk_gather 
     p.my_path_total = shard->path_total;
     p.my_json_total = shard->json_total;
     p.flag = ctx->h_gather_flag;
-    regk_gather_push_kernel<<<(unsigned)ctx->sm_count * 4, 256, 0, ctx->stream>>>(p);
+    regk_gather_push_kernel<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(p);
     CK(cudaGetLastError());
     return REGK_OK;
 }

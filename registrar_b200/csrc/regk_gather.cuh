@@ -56,20 +56,35 @@ __device__ __forceinline__ void push_bytes(const uint8_t *__restrict__ src, unsi
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);
     if (body_hi > body_lo) {
         const unsigned long long nblk = (body_hi - body_lo) >> 4;
-        for (unsigned long long b = tid; b < nblk; b += nthreads) {
-            const unsigned long long d = body_lo + (b << 4);    /* job byte of this block */
-            const unsigned long long so = d - base;             /* its source byte */
-            const uint32_t *p = sw + (so >> 2);
-            const uint32_t sh = ((uint32_t)so & 3u) * 8u;
-            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
-            const uint32_t w4 = sh ? __ldg(p + 4) : 0u;         /* aligned source: the fifth word may not exist */
-            uint4 v;
-            v.x = __funnelshift_r(w0, w1, sh);
-            v.y = __funnelshift_r(w1, w2, sh);
-            v.z = __funnelshift_r(w2, w3, sh);
-            v.w = __funnelshift_r(w3, w4, sh);
-            for (uint32_t q = 0; q < world; q++)
-                stg_v4_sys(dst[q] + d, v);
+        /* UNROLL blocks per thread and trip: all their loads are issued before the first store, so a thread
+           keeps UNROLL x world 16-byte stores in flight - NVLink round trips are microseconds long */
+        constexpr int UNROLL = 4;
+        for (unsigned long long b0 = tid; b0 < nblk; b0 += nthreads * UNROLL) {
+            uint4 v[UNROLL];
+            #pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const unsigned long long b = b0 + (unsigned long long)u * nthreads;
+                if (b < nblk) {
+                    const unsigned long long so = body_lo + (b << 4) - base;    /* source byte of this block */
+                    const uint32_t *p = sw + (so >> 2);
+                    const uint32_t sh = ((uint32_t)so & 3u) * 8u;
+                    const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
+                    const uint32_t w4 = sh ? __ldg(p + 4) : 0u;         /* aligned source: the fifth word may not exist */
+                    v[u].x = __funnelshift_r(w0, w1, sh);
+                    v[u].y = __funnelshift_r(w1, w2, sh);
+                    v[u].z = __funnelshift_r(w2, w3, sh);
+                    v[u].w = __funnelshift_r(w3, w4, sh);
+                }
+            }
+            #pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const unsigned long long b = b0 + (unsigned long long)u * nthreads;
+                if (b < nblk) {
+                    const unsigned long long d = body_lo + (b << 4);    /* job byte of this block */
+                    for (uint32_t q = 0; q < world; q++)
+                        stg_v4_sys(dst[q] + d, v[u]);
+                }
+            }
         }
     }
     /* head and tail: at most 15 bytes each (or the whole shard when it holds no aligned block) */
