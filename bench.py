@@ -42,7 +42,7 @@ NB = 4                      # distinct resident batches rotated through the time
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
 # workload (profiles/); None until a capture of the current kernels exists.
 TIME_EVERY = int(os.environ.get("REGK_TIME_EVERY", "8"))
-NCU_TRAFFIC = {"path": 104845824, "json": 68146944}    # profiles/r1_ncu_final.txt (config2, 1M records)
+NCU_TRAFFIC = {"path": 104491008, "json": 68337664}    # profiles/r1_ncu_final.txt (config2, 1M records)
 
 
 def load_peaks():

@@ -19,4 +19,15 @@ check(RecordBatch.from_records(recs))                    # variable hostnames + 
 check(RecordBatch.from_records(recs, alias=True))
 ctx.set_option("force_generic", 1); check(synth.generate("config3", n=1000)); ctx.set_option("force_generic", 0)
 ctx.set_option("chunk_records", 512); check(synth.generate("config3", n=3000)); ctx.set_option("chunk_records", 262144)
+# async host batches, two in flight (alternating staging / result sets)
+ctx.set_option("async", 1)
+b1, b2 = synth.generate("config2", n=2000, start=5), synth.generate("config5", n=1700, start=9)
+t1 = ctx.submit(b1); t2 = ctx.submit(b2)
+for t, b in ((t1, b1), (t2, b2)):
+    got = ctx.collect(t, copy=True); want = oracle.register_batch(b)
+    assert np.array_equal(got.path_bytes, want.path_bytes) and np.array_equal(got.json_bytes, want.json_bytes)
+ctx.set_option("async", 0)
+# a one-record last tile (head/tail byte stores only)
+check(RecordBatch.from_records([{"domain": b"ab.cd", "hostname": b"h" * 9, "type": b"host", "address": b"10.0.0.1"}] * 128 +
+                               [{"domain": b"ab.cd", "hostname": b"x" * 13, "type": b"host", "address": b"10.0.0.1"}]))
 print("sanitize_run ok")
