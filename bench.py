@@ -38,7 +38,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "service-records/sec"
 UNIT = "records/s"
-NB = 4                      # distinct resident batches rotated through the timed loop
+NB_DEFAULT = 4              # distinct resident batches rotated through the timed loop (2 for batches > 2 M records)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
 # workload (profiles/); None until a capture of the current kernels exists.
 TIME_EVERY = int(os.environ.get("REGK_TIME_EVERY", "8"))
@@ -168,6 +168,7 @@ def run_b200(args):
     ctx.set_stream(stream.cuda_stream)
 
     # ---- workload: NB distinct shards per rank, generated on the host, moved to HBM once ----
+    NB = NB_DEFAULT if n <= 2_000_000 else 2
     host_batches = [synth.generate(cfg, n=n, start=(rank * NB + b) * n) for b in range(NB)]
     ctx.set_types(host_batches[0].types)
     keep, cbatches = [], []
@@ -332,7 +333,7 @@ def run_b200(args):
 
         roofs = {"path": roof("regk_path_kernel<false>", pb, p_ms), "json": roof("regk_json_kernel", jb, j_ms)}
         for k in roofs:
-            roofs[k]["traffic"] = NCU_TRAFFIC.get(k)
+            roofs[k]["traffic"] = NCU_TRAFFIC.get(k) if (cfg, n) == ("config2", 1_000_000) else None
         dominant = "path" if p_ms >= j_ms else "json"
         both = (pb + jb) / ((p_ms + j_ms) * 1e-3) / 1e9 if p_ms + j_ms > 0 else 0.0
         line = {

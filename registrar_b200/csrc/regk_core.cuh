@@ -747,13 +747,27 @@ RG_HD uint32_t ndigits4(uint32_t r)                          /* r < 10000 */
     return 1u + (r >= 10u) + (r >= 100u) + (r >= 1000u);
 }
 
+/* decimal digits of any uint32, branch-free: floor(log10) estimated from the bit length (1233/4096 ~ log10 2),
+   corrected by one table compare.  (v | 1 keeps 0 at one digit; 10^t - 1 is odd, so the `| 1` changes no answer.) */
+#if defined(__CUDACC__)
+__device__ __constant__ uint32_t regk_pow10_dev[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u,
+                                                       100000000u, 1000000000u};
+#endif
+RG_HD uint32_t pow10_u32(uint32_t t)                        /* t in 0..9 */
+{
+#if defined(__CUDA_ARCH__)
+    return regk_pow10_dev[t];                               /* constant bank, not a stack array */
+#else
+    static const uint32_t p10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+    return p10[t];
+#endif
+}
+
 RG_HD uint32_t ndigits_u32(uint32_t v)
 {
-    if (v < 10000u)
-        return ndigits4(v);
-    if (v < 100000000u)
-        return 4u + ndigits4(v / 10000u);
-    return 8u + ndigits4(v / 100000000u);
+    const uint32_t w = v | 1u;
+    const uint32_t t = ((32u - clz32(w)) * 1233u) >> 12;    /* 0..9 */
+    return t + 1u - (w < pow10_u32(t) ? 1u : 0u);
 }
 
 /* Number::toString for an unsigned 32-bit integer (ports, |ttl|). */
@@ -778,10 +792,15 @@ RG_HD void put_u32_dec(uint32_t v, Sink &sink)
     sink.put4(dec4(r));
 }
 
+/* ttl: small values dominate (30, 60, 3600 ...), so the four-compare short cut comes first; the branch is
+   almost always uniform across a warp */
 RG_HD uint32_t ndigits_i32(int32_t v)
 {
-    uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
-    return ndigits_u32(u) + (v < 0 ? 1u : 0u);
+    const uint32_t u = v < 0 ? 0u - (uint32_t)v : (uint32_t)v;
+    const uint32_t neg = v < 0 ? 1u : 0u;
+    if (u < 10000u)
+        return ndigits4(u) + neg;
+    return ndigits_u32(u) + neg;
 }
 
 template <class Sink>

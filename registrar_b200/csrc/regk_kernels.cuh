@@ -321,9 +321,17 @@ __device__ __forceinline__ JsonMeta json_meta(const JsonParams &p, uint64_t r)
 
 __device__ __forceinline__ uint32_t json_meta_len(const JsonParams &p, const JsonMeta &m, const TypeFrag &tf)
 {
+    /* up to four port values by predicated loads issued together (SRV records rarely carry more), then a loop */
+    const uint32_t *pp = p.ports + m.p0;
+    const uint32_t k = m.k;
     uint32_t port_digits = 0;
-    for (uint32_t i = 0; i < m.k; i++)
-        port_digits += ndigits_u32(p.ports[m.p0 + i]);
+    if (k) {                                                /* skipped by warps whose records carry no ports */
+        const uint32_t v0 = pp[0], v1 = k > 1u ? pp[1] : 0u, v2 = k > 2u ? pp[2] : 0u, v3 = k > 3u ? pp[3] : 0u;
+        port_digits = ndigits_u32(v0) + (k > 1u ? ndigits_u32(v1) : 0u) + (k > 2u ? ndigits_u32(v2) : 0u) +
+                      (k > 3u ? ndigits_u32(v3) : 0u);
+        for (uint32_t i = 4; i < k; i++)
+            port_digits += ndigits_u32(pp[i]);
+    }
     return json_length(tf.f1_len, tf.f2_len, m.al, m.has_ttl, m.ttl, m.has_ports, m.k, port_digits);
 }
 

@@ -115,7 +115,8 @@ def test_alias_nodes_keep_empty_labels(emul, generic):
 def test_decimal(emul):
     out = (C.c_uint8 * 16)()
     vals = list(range(0, 12000)) + [99999, 100000, 655350, 9999999, 10000000, 99999999, 100000000, 123456789,
-                                    999999999, 1000000000, 4294967295, 2147483648]
+                                    999999999, 1000000000, 4294967295, 2147483648, 65535, 65536, 999999, 1000000, 16777215,
+                                    16777216, 1073741823, 1073741824, 4294967294]
     rng = np.random.default_rng(1)
     vals += [int(x) for x in rng.integers(0, 2 ** 32, 5000)]
     for v in vals:
