@@ -3,6 +3,7 @@ reassembled on every rank (regk_gather_push over NVLink peer memory), gathered s
 with the single-GPU stream.  Launch:  python -m torch.distributed.run --nproc-per-node W tools/config4_run.py
 [--records 10000000].  Rank 0 prints one JSON line."""
 import argparse
+import faulthandler
 import json
 import os
 import sys
@@ -18,6 +19,7 @@ from registrar_b200.batch import FLAG_OUT_DEVICE
 
 
 def main():
+    faulthandler.enable()
     ap = argparse.ArgumentParser()
     ap.add_argument("--records", type=int, default=10_000_000)
     ap.add_argument("--config", default="config3")
@@ -102,7 +104,9 @@ def main():
     flag = torch.tensor([1 if identical else 0], dtype=torch.int32, device=dev)
     dist.broadcast(flag, 0)
     recv = g.nbytes_received
-    pg.close()
+    path_total, json_total = int(g.path_off[N]), int(g.json_off[N])
+    del g
+    pg.close()                                       # unmaps and frees the whole-job buffers: no views beyond this point
     if rank == 0:
         print(json.dumps({
             "what": "BASELINE configs[3]: %s, %d records sharded over %d GPUs, all-gather-v over NVLink peer memory"
@@ -112,7 +116,7 @@ def main():
             "kernels_ms_max_rank": kernel_ms, "gather_ms": gather_ms, "recv_bytes_per_rank": recv,
             "recv_GBps_per_rank": recv / (gather_ms * 1e-3) / 1e9,
             "records_per_s_kernels_plus_gather": N / ((kernel_ms + gather_ms) * 1e-3),
-            "path_bytes": int(g.path_off[N]), "json_bytes": int(g.json_off[N])}), flush=True)
+            "path_bytes": path_total, "json_bytes": json_total}), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if (identical or rank != 0) and same_everywhere and int(flag[0]) == 1 else 1)
 
