@@ -203,6 +203,28 @@ typedef struct regk_gather {
  * at regk_sync time through the returned device flag, never a wild store. */
 int         regk_gather_push(regk_ctx *ctx, const regk_result *shard, const regk_gather *g);
 
+/*
+ * ---- setupDirectories for a batch (reference lib/register.js:107-125: mkdirp(path.dirname(n)) for every node) ----
+ * Works on the path stream of the batch most recently finished on this context (its device copy is still in
+ * the context).  parent_len[i] = byte length of path.dirname(path_i), always a prefix of path_i (node >= 6
+ * posix semantics: '/' for a top-level node, '//' when the last separator sits at index 1); unique_first[] =
+ * record index of the first occurrence of every DISTINCT directory, ascending - the set a batched mkdirp
+ * needs (10^7 instances share ~10^3 parents).  Directories are compared byte for byte; hashing only picks a
+ * table slot.  flags: REGK_OUT_DEVICE returns device pointers, otherwise pinned host arrays; both stay valid
+ * until the next regk_parent_dirs call on the context.
+ */
+typedef struct regk_parents {
+    uint64_t n;                     /* records of the batch */
+    uint64_t n_unique;
+    uint32_t flags;
+    uint32_t launches;
+    const uint32_t *parent_len;     /* [n] */
+    const uint64_t *unique_first;   /* [n_unique] */
+    float kernel_ms;
+} regk_parents;
+
+int         regk_parent_dirs(regk_ctx *ctx, uint32_t flags, regk_parents *out);
+
 /* Tuning knobs (kernel variant selection for A/B measurement); see DESIGN.md. */
 int         regk_set_option(regk_ctx *ctx, const char *name, int64_t value);
 int64_t     regk_get_option(const regk_ctx *ctx, const char *name);

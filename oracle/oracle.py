@@ -173,6 +173,26 @@ def register_batch(batch, threads: int = 0, flags_extra: int = 0, timing_only: b
     return r
 
 
+def parent_dirs(result):
+    """setupDirectories over a batch result (lib/register.js:107-125): (parent_len[n], unique_first[]) where
+    parent_len[i] = len(path.dirname(path_i)) and unique_first lists, ascending, the record index of the first
+    occurrence of every distinct directory.  Also checks that dirname is a prefix of the path."""
+    n = result.n
+    plen = np.zeros(n, np.uint32)
+    seen, firsts = {}, []
+    pb = result.path_bytes.tobytes()
+    off = result.path_off
+    for i in range(n):
+        p = pb[int(off[i]):int(off[i + 1])]
+        d = posix_dirname(p)
+        assert p.startswith(d), (p, d)
+        plen[i] = len(d)
+        if d not in seen:
+            seen[d] = i
+            firsts.append(i)
+    return plen, np.asarray(firsts, np.uint64)
+
+
 def max_threads() -> int:
     return int(lib().ro_max_threads())
 

@@ -72,11 +72,16 @@ class CGather(C.Structure):          # regk_gather
                 ("path_cap", C.c_uint64), ("json_cap", C.c_uint64)]
 
 
+class CParents(C.Structure):         # regk_parents
+    _fields_ = [("n", C.c_uint64), ("n_unique", C.c_uint64), ("flags", C.c_uint32), ("launches", C.c_uint32),
+                ("parent_len", C.c_void_p), ("unique_first", C.c_void_p), ("kernel_ms", C.c_float)]
+
+
 EXPORTS = ["regk_abi_version", "regk_create", "regk_destroy", "regk_last_error", "regk_set_stream",
            "regk_set_types", "regk_register_batch", "regk_finish", "regk_release", "regk_host_alloc",
            "regk_host_free", "regk_dev_alloc", "regk_dev_free", "regk_memcpy_h2d", "regk_memcpy_d2h",
            "regk_sync", "regk_set_option", "regk_get_option", "regk_ipc_export", "regk_ipc_open", "regk_ipc_close",
-           "regk_gather_push"]
+           "regk_gather_push", "regk_parent_dirs"]
 
 _lib = None
 
@@ -121,6 +126,7 @@ def load_library():
     lib.regk_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.regk_ipc_close.argtypes = [vp, vp]
     lib.regk_gather_push.argtypes = [vp, C.POINTER(CResult), C.POINTER(CGather)]
+    lib.regk_parent_dirs.argtypes = [vp, u32, C.POINTER(CParents)]
     _lib = lib
     return lib
 
@@ -310,6 +316,19 @@ class Context:
     def finish(self, cres: CResult) -> CResult:
         self._check(self._lib.regk_finish(self._h, C.byref(cres)), cres)
         return cres
+
+    # -- setupDirectories for the batch finished last (lib/register.js:107-125) --
+    def parent_dirs(self, device: bool = False):
+        """(parent_len uint32[n], unique_first uint64[n_unique], kernel_ms) for the batch finished last on this
+        context: the length of path.dirname(path_i) (always a prefix of path_i) and the record index of the first
+        occurrence of every distinct directory, ascending.  device=True returns the raw CParents (device pointers)."""
+        out = CParents()
+        self._check(self._lib.regk_parent_dirs(self._h, FLAG_OUT_DEVICE if device else 0, C.byref(out)))
+        if device:
+            return out
+        n, nu = int(out.n), int(out.n_unique)
+        return (_as_np(out.parent_len, n, np.uint32).copy(), _as_np(out.unique_first, nu, np.uint64).copy(),
+                float(out.kernel_ms))
 
     # -- multi-GPU reassembly (regk_gather_push over CUDA-IPC mapped peer buffers) --
     def dev_alloc(self, nbytes: int) -> int:

@@ -21,6 +21,7 @@
 #include "../../include/regk.h"
 #include "regk_kernels.cuh"
 #include "regk_gather.cuh"
+#include "regk_parents.cuh"
 #include "regk_types.hpp"
 
 using namespace regk;
@@ -73,6 +74,12 @@ struct regk_ctx {
     HostSet hset[2];
     uint64_t hseq = 0;
     uint32_t *h_gather_flag = nullptr;          /* pinned: regk_gather_push found the whole-job buffers too small */
+    /* device copy of the path stream of the batch finished last (regk_parent_dirs works on it) */
+    const uint8_t *last_path_bytes = nullptr;
+    const unsigned long long *last_path_off = nullptr;
+    uint64_t last_n = 0;
+    DevBuf par_len, par_slot, par_table, par_totals, par_unique;
+    HostBuf h_par_len, h_par_unique, h_par_count;
     std::vector<cudaEvent_t> pipe_events;
     /* workspace: DevStatus | two-level byte totals of both halves (stream-ordered reuse; host pipelining) */
     DevBuf work;
@@ -99,6 +106,8 @@ struct regk_ctx {
         int hset = -1;                          /* async host batch: which HostSet it lives in */
         bool d2h_issued = false;
         bool timed = true;                      /* ev[0..2] were recorded for this batch */
+        const uint8_t *dev_path_bytes = nullptr;        /* where this batch's path stream lives on the device */
+        const unsigned long long *dev_path_off = nullptr;
         bool in_use = false;
         uint64_t n = 0;
         uint32_t flags = 0;
@@ -561,6 +570,12 @@ void regk_destroy(regk_ctx *ctx)
         cudaFreeHost(ctx->h_status_block);
     if (ctx->h_gather_flag)
         cudaFreeHost(ctx->h_gather_flag);
+    for (DevBuf *b : {&ctx->par_len, &ctx->par_slot, &ctx->par_table, &ctx->par_totals, &ctx->par_unique})
+        if (b->p)
+            cudaFree(b->p);
+    for (HostBuf *b : {&ctx->h_par_len, &ctx->h_par_unique, &ctx->h_par_count})
+        if (b->p)
+            cudaFreeHost(b->p);
     for (auto &sl : ctx->slots)
         for (auto &ev : sl.ev)
             if (ev)
@@ -1059,6 +1074,11 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             hp.dev[i] = need[i] && src[i] ? ctx->in[i].p : nullptr;
         }
         rc = run_pipelined(ctx, b, res, pp, path_smem, jp, json_smem, hp);
+        if (rc == REGK_OK) {
+            ctx->last_path_bytes = do_path ? pp.out_bytes : nullptr;
+            ctx->last_path_off = do_path ? pp.out_off : nullptr;
+            ctx->last_n = do_path ? n : 0;
+        }
         if (rc != REGK_ERR_STATE + 100)         /* anything but "needs the exact redo" */
             return rc;
         /* some domain has empty labels: run the whole batch again through the regular (exact-capable) path */
@@ -1071,6 +1091,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     uint32_t launches = 0;
     slot.did_path = false;
     slot.d_status = d_status;
+    slot.dev_path_bytes = (n && do_path) ? pp.out_bytes : nullptr;
+    slot.dev_path_off = (n && do_path) ? pp.out_off : nullptr;
     const bool fused_len = n && do_path && do_json;
     /* per-kernel timing events sit between the launches and cost a few microseconds of stream gaps per batch:
        "time_every" = K keeps them on every K-th batch only (the others report kernel times of 0) */
@@ -1206,6 +1228,9 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     const DevStatus st = *slot->h_status;
     const uint64_t n = slot->n;
     const bool out_dev = slot->flags & REGK_OUT_DEVICE;
+    ctx->last_path_bytes = st.bad_bits ? nullptr : slot->dev_path_bytes;
+    ctx->last_path_off = st.bad_bits ? nullptr : slot->dev_path_off;
+    ctx->last_n = (st.bad_bits || !slot->dev_path_off) ? 0 : n;
     float ms_p = 0, ms_jl = 0, ms_j = 0;
     if (slot->timed) {
         cudaEventElapsedTime(&ms_p, slot->ev[0], slot->ev[1]);
@@ -1275,6 +1300,87 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     res->path_off = (uint64_t *)ctx->h_path_off.p;
     res->json_bytes = (uint8_t *)ctx->h_json_bytes.p;
     res->json_off = (uint64_t *)ctx->h_json_off.p;
+    return REGK_OK;
+}
+
+int regk_parent_dirs(regk_ctx *ctx, uint32_t flags, regk_parents *out)
+{
+    if (!ctx || !out)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_parent_dirs: NULL argument");
+    memset(out, 0, sizeof *out);
+    if (ctx->pending)
+        return fail(ctx, REGK_ERR_STATE, "regk_parent_dirs: batches are still in flight; finish them first");
+    if (!ctx->last_path_off || !ctx->last_path_bytes)
+        return fail(ctx, REGK_ERR_STATE, "regk_parent_dirs: no finished batch with a path stream on this context");
+    const uint64_t n = ctx->last_n;
+    if (n >= 0xFFFFFFFEull)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_parent_dirs: batch too large");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool dev_out = flags & REGK_OUT_DEVICE;
+    out->n = n;
+    out->flags = dev_out ? REGK_OUT_DEVICE : 0;
+    if (n == 0)
+        return REGK_OK;
+    uint64_t slots = 1024;
+    while (slots < 2 * n)
+        slots <<= 1;
+    const uint64_t ntiles = (n + PARENT_TILE - 1) / PARENT_TILE;
+    const size_t totals_bytes = ((ntiles * 4 + 15) & ~(size_t)15) + (ntiles / SUPER + 1) * 8 + 16;
+    int rc;
+    if ((rc = ensure_dev(ctx, ctx->par_len, n * 4)) || (rc = ensure_dev(ctx, ctx->par_slot, n * 4)) ||
+        (rc = ensure_dev(ctx, ctx->par_table, slots * 8)) || (rc = ensure_dev(ctx, ctx->par_totals, totals_bytes)) ||
+        (rc = ensure_dev(ctx, ctx->par_unique, n * 8 + 8)) || (rc = ensure_host(ctx, ctx->h_par_count, 8)))
+        return rc;
+    ParentParams p{};
+    p.n = n;
+    p.path_bytes = ctx->last_path_bytes;
+    p.path_off = ctx->last_path_off;
+    p.parent_len = (uint32_t *)ctx->par_len.p;
+    p.slot_of = (uint32_t *)ctx->par_slot.p;
+    p.owner = (uint32_t *)ctx->par_table.p;
+    p.first = p.owner + slots;
+    p.mask = (uint32_t)(slots - 1);
+    p.tile_total = (uint32_t *)ctx->par_totals.p;
+    p.super_total = (unsigned long long *)((uint8_t *)ctx->par_totals.p + ((ntiles * 4 + 15) & ~(size_t)15));
+    p.unique_first = (unsigned long long *)ctx->par_unique.p;
+    p.n_unique = p.unique_first + n;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaMemsetAsync(p.owner, 0, slots * 4, s));
+    CK(cudaMemsetAsync(p.first, 0xFF, slots * 4, s));
+    CK(cudaMemsetAsync(ctx->par_totals.p, 0, totals_bytes, s));
+    CK(cudaEventRecord(e0, s));
+    regk_parent_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);
+    regk_parent_mark_kernel<<<(unsigned)ntiles, PARENT_TILE, 0, s>>>(p);
+    regk_parent_compact_kernel<<<(unsigned)ntiles, PARENT_TILE, 0, s>>>(p);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, s));
+    CK(cudaMemcpyAsync(ctx->h_par_count.p, p.n_unique, 8, cudaMemcpyDeviceToHost, s));
+    cudaError_t e = cudaStreamSynchronize(s);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess)
+        return fail(ctx, REGK_ERR_CUDA, "regk_parent_dirs: kernel execution failed: %s", cudaGetErrorString(e));
+    const uint64_t nu = *(const unsigned long long *)ctx->h_par_count.p;
+    out->n_unique = nu;
+    out->launches = 3;
+    out->kernel_ms = ms;
+    if (dev_out) {
+        out->parent_len = p.parent_len;
+        out->unique_first = (const uint64_t *)p.unique_first;
+        return REGK_OK;
+    }
+    if ((rc = ensure_host(ctx, ctx->h_par_len, n * 4)) || (rc = ensure_host(ctx, ctx->h_par_unique, nu * 8 + 8)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->h_par_len.p, p.parent_len, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_par_unique.p, p.unique_first, nu * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    out->parent_len = (const uint32_t *)ctx->h_par_len.p;
+    out->unique_first = (const uint64_t *)ctx->h_par_unique.p;
     return REGK_OK;
 }
 

@@ -1,0 +1,163 @@
+/*
+ * regk_parents.cuh — setupDirectories for a batch (reference lib/register.js:107-125):
+ *     opts.nodes.map(function (p) { return (path.dirname(p)); })   ->   zk.mkdirp() of each
+ * For N node paths the reference would issue N mkdirp calls, almost all for the same few directories
+ * (10^7 instances of a service share ~10^3 parents).  This pass computes, on the GPU, from the packed path
+ * stream the registration kernels just wrote:
+ *   parent_len[i]   the byte length of path.dirname(path_i) - always a PREFIX of path_i (node >= 6 posix
+ *                   dirname: everything before the last '/' that precedes the final segment, trailing
+ *                   slashes skipped; '/' when there is none; '//' when that slash is at index 1);
+ *   unique_first[]  the record index of the first occurrence of every distinct directory, ascending -
+ *                   the exact set a batched mkdirp needs, byte-compared (hashing only picks the slot).
+ *
+ * Kernels: (1) regk_parent_kernel - one thread per record: backward scan for the directory length, 64-bit
+ * hash of the prefix, insert into an open-addressing table whose slots hold "owner record + 1" (claimed by
+ * one atomicCAS, so the owner is stable the moment it is visible); a record that meets a claimed slot
+ * compares its prefix with the owner's bytes - equal: same directory (atomicMin of the first index),
+ * different: next slot.  (2) regk_parent_mark_kernel - a record is a first occurrence iff the table says
+ * so; per-tile counts go into two-level totals.  (3) regk_parent_compact_kernel - each tile derives its base
+ * from the totals and writes its first-occurrence indices in order.
+ */
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace regk {
+
+struct ParentParams {
+    uint64_t n;
+    const uint8_t *path_bytes;
+    const unsigned long long *path_off;         /* [n + 1] */
+    uint32_t *parent_len;                       /* [n] */
+    uint32_t *slot_of;                          /* [n] the table slot of record i's directory */
+    uint32_t *owner;                            /* [slots] record + 1, 0 = empty (zeroed by the host) */
+    uint32_t *first;                            /* [slots] smallest record index with this directory (0xFFFFFFFF-filled) */
+    uint32_t mask;                              /* slots - 1 (power of two) */
+    uint32_t *tile_total;                       /* [ntiles] first occurrences per tile */
+    unsigned long long *super_total;            /* [ntiles / SUPER + 1] */
+    unsigned long long *unique_first;           /* out: ascending record indices */
+    unsigned long long *n_unique;               /* out */
+};
+
+/* node (>= 6) posix path.dirname on an absolute path of n >= 1 bytes: the length of the directory prefix */
+__device__ __forceinline__ uint32_t dirname_len(const uint8_t *p, uint32_t n)
+{
+    bool matched_slash = true;
+    for (uint32_t i = n - 1; i >= 1; --i) {
+        if (p[i] == '/') {
+            if (!matched_slash)
+                return i == 1 ? 2u : i;                     /* '//' when the separator sits at index 1 */
+        } else {
+            matched_slash = false;
+        }
+    }
+    return 1;                                               /* no separator beyond the root: '/' */
+}
+
+__device__ __forceinline__ unsigned long long hash_bytes(const uint8_t *p, uint32_t n)
+{
+    unsigned long long h = 0x9E3779B97F4A7C15ull ^ n;
+    for (uint32_t i = 0; i < n; i++) {
+        h ^= p[i];
+        h *= 0x100000001B3ull;                              /* FNV-1a step */
+    }
+    h ^= h >> 32;
+    h *= 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    return h;
+}
+
+__device__ __forceinline__ bool same_bytes(const uint8_t *a, const uint8_t *b, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; i++)
+        if (a[i] != b[i])
+            return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) regk_parent_kernel(const ParentParams p)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n)
+        return;
+    const unsigned long long o0 = p.path_off[i], o1 = p.path_off[i + 1];
+    const uint8_t *mine = p.path_bytes + o0;
+    const uint32_t len = (uint32_t)(o1 - o0);
+    const uint32_t plen = len ? dirname_len(mine, len) : 0u;
+    p.parent_len[i] = plen;
+    uint32_t slot = (uint32_t)hash_bytes(mine, plen) & p.mask;
+    for (;;) {
+        uint32_t cur = p.owner[slot];
+        if (cur == 0u) {
+            cur = atomicCAS(p.owner + slot, 0u, (uint32_t)i + 1u);
+            if (cur == 0u)
+                break;                                      /* claimed: this record owns the slot */
+        }
+        const uint64_t j = cur - 1u;                        /* the owner is final once visible */
+        if (j == i)
+            break;
+        /* compare with the owner's directory, derived from its own path (its parent_len may not be stored yet) */
+        const unsigned long long q0 = p.path_off[j], q1 = p.path_off[j + 1];
+        const uint8_t *theirs = p.path_bytes + q0;
+        const uint32_t tlen = (uint32_t)(q1 - q0);
+        const uint32_t tpl = tlen ? dirname_len(theirs, tlen) : 0u;
+        if (tpl == plen && same_bytes(mine, theirs, plen))
+            break;                                          /* same directory */
+        slot = (slot + 1u) & p.mask;
+    }
+    p.slot_of[i] = slot;
+    if (p.first[slot] > (uint32_t)i)
+        atomicMin(p.first + slot, (uint32_t)i);
+}
+
+constexpr uint32_t PARENT_TILE = 256;
+
+__global__ void __launch_bounds__(PARENT_TILE) regk_parent_mark_kernel(const ParentParams p)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * PARENT_TILE + threadIdx.x;
+    uint32_t is_first = 0;
+    if (i < p.n)
+        is_first = p.first[p.slot_of[i]] == (uint32_t)i ? 1u : 0u;
+    uint32_t cnt = __popc(__ballot_sync(0xFFFFFFFFu, is_first));
+    if ((threadIdx.x & 31u) == 0)
+        add_tile_total(p.tile_total, p.super_total, blockIdx.x, cnt);
+}
+
+__global__ void __launch_bounds__(PARENT_TILE) regk_parent_compact_kernel(const ParentParams p)
+{
+    __shared__ uint32_t warp_sum[PARENT_TILE / 32];
+    __shared__ unsigned long long s_base;
+    const uint32_t tile = blockIdx.x;
+    if (threadIdx.x < 32) {
+        const unsigned long long b = tile_base_from_totals(p.tile_total, p.super_total, tile);
+        if (threadIdx.x == 0)
+            s_base = b;
+    }
+    const uint64_t i = (uint64_t)tile * PARENT_TILE + threadIdx.x;
+    uint32_t is_first = 0;
+    if (i < p.n)
+        is_first = p.first[p.slot_of[i]] == (uint32_t)i ? 1u : 0u;
+    __syncthreads();
+    /* block-wide exclusive scan of the flags (same shape as block_scan in regk_kernels.cuh, 8 warps) */
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, is_first);
+    const uint32_t before_lane = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0)
+        warp_sum[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before_warp = 0, total = 0;
+    #pragma unroll
+    for (uint32_t w = 0; w < PARENT_TILE / 32; w++) {
+        const uint32_t sct = warp_sum[w];
+        if (w < warp)
+            before_warp += sct;
+        total += sct;
+    }
+    if (is_first)
+        p.unique_first[s_base + before_warp + before_lane] = i;
+    if (i + 1 == p.n)                                       /* the thread of the last record closes the list */
+        *p.n_unique = s_base + total;
+}
+
+}  // namespace regk

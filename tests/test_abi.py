@@ -48,6 +48,7 @@ def test_struct_layouts_match_header(built):
     #include <stddef.h>
     #include "regk.h"
     int main(void) {
+        printf("%zu %zu %zu ", sizeof(regk_parents), offsetof(regk_parents, unique_first), offsetof(regk_parents, kernel_ms));
         printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(regk_batch), offsetof(regk_batch, domain_bytes),
                offsetof(regk_batch, ports_present), sizeof(regk_result), offsetof(regk_result, json_total),
                offsetof(regk_result, opaque), sizeof(regk_gather), offsetof(regk_gather, totals),
@@ -58,7 +59,8 @@ def test_struct_layouts_match_header(built):
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
-    got = [C.sizeof(_native.CBatch), _native.CBatch.domain_bytes.offset, _native.CBatch.ports_present.offset,
+    got = [C.sizeof(_native.CParents), _native.CParents.unique_first.offset, _native.CParents.kernel_ms.offset,
+           C.sizeof(_native.CBatch), _native.CBatch.domain_bytes.offset, _native.CBatch.ports_present.offset,
            C.sizeof(_native.CResult), _native.CResult.json_total.offset, _native.CResult.opaque.offset,
            C.sizeof(_native.CGather), _native.CGather.totals.offset, _native.CGather.json_off.offset,
            _native.CGather.json_cap.offset]

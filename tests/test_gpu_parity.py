@@ -314,6 +314,57 @@ def test_random_batches_of_every_shape(ctx, seed):
             ctx.set_option("force_generic", 0)
 
 
+# ---- setupDirectories for a batch: dirname lengths and the distinct directory set (regk_parent_dirs) ----
+
+def _check_parents(ctx, batch):
+    got = ctx.register_batch(batch)
+    want = oracle.register_batch(batch)
+    assert_same(got, want)
+    plen, firsts, ms = ctx.parent_dirs()
+    wlen, wfirsts = oracle.parent_dirs(want)
+    assert np.array_equal(plen, wlen)
+    assert np.array_equal(firsts, wfirsts)
+    return got, plen, firsts
+
+
+def test_parent_dirs_synthetic(ctx):
+    # config 3 at 50 000 records: a few hundred thousand label draws, almost every directory distinct
+    _check_parents(ctx, synth.generate("config3", n=50_000, start=11))
+    # few directories, many instances each (the case the pass exists for)
+    recs = [{"domain": b"svc%d.dc%d.example.com" % (i % 37, i % 3), "hostname": b"%08x-0000-4000-8000-%012x" % (i, i),
+             "type": b"host", "address": b"10.0.0.1"} for i in range(20_000)]
+    got, plen, firsts = _check_parents(ctx, RecordBatch.from_records(recs))
+    assert len(firsts) == 37 * 3
+    dirs = {got.path(int(f))[:int(plen[int(f)])] for f in firsts}
+    assert b"/com/example/dc0/svc0" in dirs and len(dirs) == 111
+
+
+def test_parent_dirs_edge_paths(ctx):
+    # alias nodes keep empty labels: '/b//a' -> '/b/', '//a' -> '//', '/' -> '/', trailing slashes skipped
+    doms = [b"a.b", b"a..b", b"a.", b".a", b"", b"a", b"..", b"a.b.", b".a.b", b"x.y.z", b"x.y.z", b"A.B", b"a...", b"..a..b.."]
+    alias = RecordBatch.from_records([{"domain": d, "hostname": b"h", "type": b"host", "address": b"1.1.1.1"} for d in doms],
+                                     alias=True)
+    got, plen, firsts = _check_parents(ctx, alias)
+    as_dir = lambda i: got.path(i)[:int(plen[i])]
+    assert as_dir(doms.index(b"a..b")) == b"/b/" and as_dir(doms.index(b"a.")) == b"//" and as_dir(doms.index(b"")) == b"/"
+    # host nodes: normalised paths, the directory is the reversed domain ('/' for an empty domain)
+    host = RecordBatch.from_records([{"domain": d, "hostname": b"h%d" % (i % 3), "type": b"host", "address": b"1.1.1.1"}
+                                     for i, d in enumerate(doms)])
+    got, plen, firsts = _check_parents(ctx, host)
+    assert got.path(doms.index(b""))[:int(plen[doms.index(b"")])] == b"/"
+
+
+def test_parent_dirs_needs_a_finished_path_batch(ctx):
+    from registrar_b200._native import RegkError
+    batch = synth.generate("config1")
+    ctx.register_batch(batch, paths=False)
+    with pytest.raises(RegkError):
+        ctx.parent_dirs()
+    ctx.register_batch(batch)
+    plen, firsts, ms = ctx.parent_dirs()
+    assert len(plen) == batch.n and 0 < len(firsts) <= batch.n
+
+
 # ---- host batches: chunked H2D | kernels | D2H overlap inside one call; two batches in flight with "async" ----
 
 @pytest.fixture()

@@ -113,3 +113,24 @@ def test_posix_helpers_agree(built):
         assert oracle.posix_dirname(p.encode()) == pyoracle.node_dirname(p).encode(), p
     for a, b in [("/a", "b"), ("/a/", "b"), ("/", "h"), ("/a", ""), ("", ""), ("/a/", ""), ("/b//a", "h"), ("/a", "..")]:
         assert oracle.posix_join2(a.encode(), b.encode()) == pyoracle.node_join(a, b).encode(), (a, b)
+
+
+def test_parent_dirs_oracle_follows_the_reference_mkdirp_calls(built):
+    # setupDirectories (lib/register.js:107-125): the executed reference's own mkdirp arguments pin dirname;
+    # oracle.parent_dirs is that per node plus first-occurrence dedup
+    recs = [{"domain": b"a.b.c", "hostname": b"h1", "type": b"host", "address": b"1.1.1.1"},
+            {"domain": b"a.b.c", "hostname": b"h2", "type": b"host", "address": b"1.1.1.1"},
+            {"domain": b"x.b.c", "hostname": b"h1", "type": b"host", "address": b"1.1.1.1"},
+            {"domain": b"", "hostname": b"h1", "type": b"host", "address": b"1.1.1.1"},
+            {"domain": b"a.b.c", "hostname": b"h3", "type": b"host", "address": b"1.1.1.1"}]
+    res = oracle.register_batch(RecordBatch.from_records(recs))
+    plen, firsts = oracle.parent_dirs(res)
+    dirs = [res.path(i)[:int(plen[i])] for i in range(len(recs))]
+    assert dirs == [b"/c/b/a", b"/c/b/a", b"/c/b/x", b"/", b"/c/b/a"]
+    assert [pyoracle.node_dirname(res.path(i).decode()).encode() for i in range(len(recs))] == dirs
+    assert firsts.tolist() == [0, 2, 3]
+    alias = oracle.register_batch(RecordBatch.from_records(
+        [dict(r, domain=d) for r, d in zip(recs, (b"a..b", b"a.", b"", b"a", b"a..b"))], alias=True))
+    plen, firsts = oracle.parent_dirs(alias)
+    assert [alias.path(i)[:int(plen[i])] for i in range(5)] == [b"/b/", b"//", b"/", b"/", b"/b/"]
+    assert firsts.tolist() == [0, 1, 2]

@@ -30,4 +30,9 @@ ctx.set_option("async", 0)
 # a one-record last tile (head/tail byte stores only)
 check(RecordBatch.from_records([{"domain": b"ab.cd", "hostname": b"h" * 9, "type": b"host", "address": b"10.0.0.1"}] * 128 +
                                [{"domain": b"ab.cd", "hostname": b"x" * 13, "type": b"host", "address": b"10.0.0.1"}]))
+# setupDirectories pass: hash table inserts, compaction
+b = synth.generate("config3", n=5000, start=3)
+got = ctx.register_batch(b); plen, firsts, ms = ctx.parent_dirs()
+wl, wf = oracle.parent_dirs(oracle.register_batch(b))
+assert np.array_equal(plen, wl) and np.array_equal(firsts, wf)
 print("sanitize_run ok")
