@@ -535,6 +535,14 @@ RG_HD uint32_t bit_window32(const uint32_t *bits, uint32_t pos)
     return funnel_r(bits[pos >> 5], bits[(pos >> 5) + 1], pos & 31u);
 }
 
+/* 64 bitmap bits starting at bit `pos` (the bitmap is readable two words past its end) */
+RG_HD uint64_t bit_window64(const uint32_t *bits, uint32_t pos)
+{
+    const uint32_t wi = pos >> 5, sh = pos & 31u;
+    const uint32_t w0 = bits[wi], w1 = bits[wi + 1], w2 = bits[wi + 2];
+    return ((uint64_t)funnel_r(w1, w2, sh) << 32) | funnel_r(w0, w1, sh);
+}
+
 /* bits: dot bitmap of the staged tile (readable two words past the end); b0: bit index of the domain's byte 0 */
 RG_HD DomainInfo domain_info(const uint32_t *bits, uint32_t b0, uint32_t L)
 {
@@ -641,50 +649,34 @@ RG_HD void copy_blocks(const uint32_t *w, uint32_t off, uint32_t len, WordSink &
     }
 }
 
-/* position after the last '.' strictly below relative position e of the domain whose bit 0 is bitmap bit b0, or 0 */
-RG_HD uint32_t label_start_below(const uint32_t *bits, uint32_t b0, uint32_t e)
-{
-    uint32_t pos = b0 + e;                                  /* absolute bit index, exclusive */
-    while (pos > b0) {
-        const uint32_t wi = (pos - 1u) >> 5;
-        uint32_t w = bits[wi];
-        const uint32_t top = pos - (wi << 5);               /* 1..32 bits of this word are below pos */
-        if (top < 32u)
-            w &= (1u << top) - 1u;
-        const uint32_t base = wi << 5;
-        if (base < b0)
-            w &= ~((1u << (b0 - base)) - 1u);
-        if (w)
-            return base + 32u - clz32(w) - b0;
-        if (base <= b0)
-            break;
-        pos = base;
-    }
-    return 0;
-}
-
 /*
  * Emit one znode path from pre-passed shared-memory inputs (see emit_path for the semantics).
  * `dom` holds lower-cased bytes with every '.' already rewritten to '/', and is readable from 16 bytes
  * BEFORE its nominal start (`doff` is relative to dom, the caller passes dom = staged buffer + 16 bytes).
  * Every label is copied together with the byte in front of it — the separator, already a '/'; for the
  * label at offset 0 that byte belongs to someone else and is patched to '/' in the register block — so the
- * label loop has no special cases.  Label boundaries come from the dot bitmap: for domains up to 64 bytes
- * the highest remaining dot is one clz away and is cleared after use; longer domains scan bitmap words.
+ * label loop has no special cases.  Label boundaries come from the dot bitmap: the highest remaining dot of a
+ * 64-bit window is one clz away and is cleared after use; domains longer than 64 bytes slide the window down.
  * FAST: a hostname of >= 24 bytes follows the labels, so label blocks may overshoot (put_block16).
  */
 template <bool ALIAS, bool FAST>
 RG_HD void emit_path2(const uint32_t *dom, const uint32_t *bits, uint32_t doff, uint32_t L, const DomainInfo &di,
     const uint32_t *host, uint32_t hoff, uint32_t H, WordSink &sink)
 {
+    /* Labels are found from the end with one clz per label in a 64-bit window of the dot bitmap, bit i of the
+       window = domain byte wbase + i.  Domains of up to 64 bytes have the whole bitmap in the window (wbase = 0);
+       longer ones start at their last 64 bytes and slide the window down when it runs out of dots. */
     uint32_t e = L;                                         /* end (exclusive) of the current label, relative */
-    uint64_t dots = di.dots;
+    uint32_t wbase = di.small ? 0u : L - 64u;
+    uint64_t dots = di.small ? di.dots : bit_window64(bits, doff + wbase);
     for (;;) {
-        uint32_t s;
-        if (di.small)
-            s = 64u - clz64(dots);                          /* position after the highest remaining '.', or 0 */
-        else
-            s = label_start_below(bits, doff, e);
+        while (dots == 0 && wbase != 0) {                   /* nothing left in this window: look further down */
+            const uint32_t nb = wbase < 64u ? wbase : 64u;
+            wbase -= nb;
+            const uint64_t w = bit_window64(bits, doff + wbase);
+            dots = nb >= 64u ? w : (w & ((1ull << nb) - 1ull));     /* only positions below the old window */
+        }
+        const uint32_t s = dots ? wbase + 64u - clz64(dots) : 0u;   /* position after the highest remaining '.', or 0 */
         if (ALIAS || e > s) {
             /* bytes [s-1, e): separator + label, in 16-byte register blocks */
             uint32_t off = doff + s - 1u, len = e - s + 1u;
@@ -704,8 +696,7 @@ RG_HD void emit_path2(const uint32_t *dom, const uint32_t *bits, uint32_t doff, 
         }
         if (s == 0)
             break;
-        if (di.small)
-            dots &= ~(1ull << (s - 1u));
+        dots &= ~(1ull << (s - 1u - wbase));
         e = s - 1u;
     }
     if (!ALIAS) {

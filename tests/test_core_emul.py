@@ -112,6 +112,50 @@ def test_alias_nodes_keep_empty_labels(emul, generic):
     assert want.path(EDGE_DOMAINS.index(b"")) == b"/"
 
 
+@pytest.mark.parametrize("alias", [False, True])
+def test_long_domains_slide_the_dot_window(emul, alias):
+    """Domains longer than 64 bytes: the 64-bit dot window starts at the last 64 bytes and slides down.  Dots at
+    and around every window edge, labels longer than a window, runs of empty labels, lengths 63..200."""
+    rng = np.random.default_rng(42)
+    doms = []
+    for L in list(range(60, 72)) + [100, 127, 128, 129, 130, 191, 192, 193, 200, 300, 383]:
+        doms.append(b"a" * L)                                   # one label, no dot at all
+        for k in (1, 2, 63, 64, 65, 66, L - 65, L - 64, L - 63, L - 2, L - 1):
+            if 0 <= k < L:
+                d = bytearray(b"b" * L)
+                d[k] = ord(".")
+                doms.append(bytes(d))                           # a single dot at a window edge
+        d = bytearray(b"c" * L)
+        for k in range(0, L, 7):
+            d[k] = ord(".")
+        doms.append(bytes(d))                                   # many short labels, leading dot
+        d = bytearray(b"d" * L)
+        d[L // 2:L // 2 + 3] = b"..."
+        doms.append(bytes(d))                                   # empty labels in the middle (host nodes drop them)
+    for _ in range(300):
+        L = int(rng.integers(65, 330))
+        d = bytearray(rng.choice(list(b"abcXYZ019-"), L).astype(np.uint8).tobytes())
+        for k in rng.integers(0, L, int(rng.integers(0, 9))):
+            d[int(k)] = ord(".")
+        doms.append(bytes(d))
+    recs = [{"domain": d, "hostname": b"h" * (1 + i % 40), "type": b"host", "address": b"10.0.0.1"}
+            for i, d in enumerate(doms)]
+    batch = RecordBatch.from_records(recs, alias=alias)
+    want = oracle.register_batch(batch)
+    cb, keep = host_cbatch(batch)
+    pb = np.zeros(int(want.path_off[-1]) + 64, np.uint8)
+    po = np.zeros(batch.n + 1, np.uint64)
+    fb = C.c_uint64(0)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert emul.emul_paths(C.byref(cb), 0, vp(pb), vp(po), C.byref(fb)) == 0
+    assert np.array_equal(po, want.path_off)
+    pt = int(po[-1])
+    if not np.array_equal(pb[:pt], want.path_bytes):
+        i = int(np.argmax(pb[:pt] != want.path_bytes))
+        r = int(np.searchsorted(po, i, side="right") - 1)
+        raise AssertionError("path %d differs: %r vs %r" % (r, bytes(pb[int(po[r]):int(po[r + 1])]), want.path(r)))
+
+
 def test_decimal(emul):
     out = (C.c_uint8 * 16)()
     vals = list(range(0, 12000)) + [99999, 100000, 655350, 9999999, 10000000, 99999999, 100000000, 123456789,
