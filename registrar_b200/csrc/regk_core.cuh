@@ -203,6 +203,23 @@ struct WordSink {
         carry = full ? funnel_rc(v, 0u, 32u - s) : out;
         s = full ? ns - 32u : ns;
     }
+    /* append the low n bytes (1..8) of the 64-bit little-endian value hi:lo; bytes above n must be zero */
+    RG_HD void put8(uint32_t lo, uint32_t hi, uint32_t n)
+    {
+        const uint32_t back = 32u - s;
+        const uint32_t o0 = carry | (lo << s);
+        const uint32_t o1 = funnel_rc(lo, hi, back);
+        const uint32_t o2 = funnel_rc(hi, 0u, back);
+        const uint32_t total = (s >> 3) + n;                /* 1..11 bytes pending */
+        if (total >= 4u)
+            wp[0] = o0;
+        if (total >= 8u)
+            wp[1] = o1;
+        const uint32_t nf = total >> 2;                     /* completed words: 0..2 */
+        carry = nf == 0u ? o0 : nf == 1u ? o1 : o2;
+        wp += nf;
+        s = (total & 3u) * 8u;
+    }
     RG_HD void put1(uint32_t c)
     {
         const uint32_t out = carry | (c << s);
@@ -239,6 +256,12 @@ struct ByteSink {
             *p++ = (uint8_t)(v >> (8 * k));
     }
     RG_HD void put4(uint32_t v) { put(v, 4); }
+    RG_HD void put8(uint32_t lo, uint32_t hi, uint32_t n)
+    {
+        put(lo, n < 4u ? n : 4u);
+        if (n > 4u)
+            put(hi, n - 4u);
+    }
     RG_HD void put1(uint32_t c) { *p++ = (uint8_t)c; }
     RG_HD void finish() {}
     RG_HD void tail() {}
@@ -250,6 +273,7 @@ struct CountSink {
     RG_HD void init() { n = 0; }
     RG_HD void put(uint32_t, uint32_t k) { n += k; }
     RG_HD void put4(uint32_t) { n += 4; }
+    RG_HD void put8(uint32_t, uint32_t, uint32_t k) { n += k; }
     RG_HD void put1(uint32_t) { n += 1; }
     RG_HD void finish() {}
 };
@@ -783,6 +807,36 @@ RG_HD void put_u32_dec(uint32_t v, Sink &sink)
     sink.put4(dec4(r));
 }
 
+/* One element of "ports":[...] with the comma in front of it (not for the first): values below 100000 - every
+   TCP/UDP port - are composed in registers (comma, leading digit, four SWAR digits) and appended by ONE sink
+   operation; anything larger takes the general integer path. */
+template <class Sink>
+RG_HD void put_port(uint32_t v, bool comma, Sink &sink)
+{
+    if (v >= 100000u) {
+        if (comma)
+            sink.put1(',');
+        put_u32_dec(v, sink);
+        return;
+    }
+    const uint32_t q = v / 10000u;                          /* 0..9 (a multiply-high and a shift) */
+    const uint32_t r = v - q * 10000u;
+    const uint32_t d4 = dec4(r);                            /* four ASCII digits, most significant in byte 0 */
+    const uint32_t n4 = q ? 4u : ndigits4(r);
+    uint32_t lo = d4 >> (8u * (4u - n4)), hi = 0, n = n4;   /* the low-order digits, leading zeros dropped */
+    if (q) {                                                /* five digits: the leading one goes in front */
+        hi = lo >> 24;
+        lo = (lo << 8) | (q + 0x30u);
+        n = 5u;
+    }
+    if (comma) {
+        hi = (hi << 8) | (lo >> 24);
+        lo = (lo << 8) | 0x2Cu;
+        n += 1u;
+    }
+    sink.put8(lo, hi, n);
+}
+
 /* ttl: small values dominate (30, 60, 3600 ...), so the four-compare short cut comes first; the branch is
    almost always uniform across a warp */
 RG_HD uint32_t ndigits_i32(int32_t v)
@@ -1033,11 +1087,8 @@ RG_HD void emit_json(const FSrc &blob, const TypeFrag &tf, const uint32_t (&aw)[
         sink.put4(RG_LE4('"', ',', '"', 'p'));              /* ","ports":[ */
         sink.put4(RG_LE4('o', 'r', 't', 's'));
         sink.put(RG_LE4('"', ':', '[', 0), 3);
-        for (uint32_t i = 0; i < k; i++) {
-            if (i)
-                sink.put1(',');
-            put_u32_dec(port(i), sink);
-        }
+        for (uint32_t i = 0; i < k; i++)
+            put_port(port(i), i != 0, sink);
         sink.put(RG_LE4(']', '}', '}', 0), 3);
     } else {
         sink.put(RG_LE4('"', '}', '}', 0), 3);

@@ -156,6 +156,21 @@ def test_long_domains_slide_the_dot_window(emul, alias):
         raise AssertionError("path %d differs: %r vs %r" % (r, bytes(pb[int(po[r]):int(po[r + 1])]), want.path(r)))
 
 
+@pytest.mark.parametrize("generic", [0, 1])
+def test_port_lists_at_every_byte_phase(emul, generic):
+    """ports elements are appended by one 8-byte sink operation (comma + up to five digits): every digit count,
+    the 99999 / 100000 switch to the general integer path, at every byte phase of the output word."""
+    edge = [0, 1, 9, 10, 99, 100, 999, 1000, 9999, 10000, 10001, 65535, 65536, 99999, 100000, 100001, 4294967295]
+    recs = []
+    for a in range(1, 9):                                       # address length shifts the phase
+        for i, p in enumerate(edge):
+            recs.append({"domain": b"a.b", "hostname": b"h", "type": b"host", "address": b"7" * a,
+                         "ports": [p, edge[(i + 3) % len(edge)], edge[(i + 7) % len(edge)], p]})
+            recs.append({"domain": b"a.b", "hostname": b"h", "type": b"load_balancer", "address": b"7" * a, "ttl": i,
+                         "ports": [p]})
+    check_equal(*run_emul(emul, RecordBatch.from_records(recs), generic))
+
+
 def test_decimal(emul):
     out = (C.c_uint8 * 16)()
     vals = list(range(0, 12000)) + [99999, 100000, 655350, 9999999, 10000000, 99999999, 100000000, 123456789,
