@@ -757,15 +757,17 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const J
                 bad |= BAD_ADDR_BYTE;
         }
     }
-    __syncthreads();                                            /* plan and mbarrier init are visible */
+    /* the record's length needs only its type's fragment lengths: read them from the global table (16 bytes, L2)
+       so that nobody waits for warp 0's totals or the bulk copy before the scan; the scan's own barriers publish
+       the plan and the mbarrier init */
+    const TypeFrag tf = reinterpret_cast<const TypeFrag *>(p.frag_blob)[m.tid];
+    const uint32_t len = live ? json_meta_len(p, m, tf) : 0;
+    uint32_t tot;
+    const uint32_t local = block_scan<uint32_t>(warp_sum, len, &tot);
     mbar_wait(&s_bar, 0);                                       /* fragment table has landed */
     const unsigned long long tile_base = s_plan.tile_base;
     const uint32_t tile_total = s_plan.tile_total;
     const uint32_t flags = s_plan.flags;
-    const TypeFrag tf = reinterpret_cast<const TypeFrag *>(s_blob)[m.tid];
-    const uint32_t len = live ? json_meta_len(p, m, tf) : 0;
-    uint32_t tot;
-    const uint32_t local = block_scan<uint32_t>(warp_sum, len, &tot);
     if (live)
         p.out_off[r] = tile_base + local;
 

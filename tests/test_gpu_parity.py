@@ -419,6 +419,44 @@ def test_async_host_batch_with_empty_labels_is_redone_at_collect(small_chunks):
     assert got.path(1234) == b"/b/a/h1234"
 
 
+def test_async_host_batch_outside_the_fence_fails_alone(ctx):
+    from registrar_b200._native import OutOfDomainError
+    good = synth.generate("config3", n=3000, start=21)
+    recs = [{"domain": b"svc%d.example.com" % i, "hostname": b"h", "type": b"host", "address": b"10.0.0.1"}
+            for i in range(2000)]
+    recs[777]["hostname"] = b"a/b"
+    bad = RecordBatch.from_records(recs)
+    want = oracle.register_batch(good)
+    ctx.set_option("async", 1)
+    try:
+        tb = ctx.submit(bad)
+        tg = ctx.submit(good)
+        with pytest.raises(OutOfDomainError) as ei:
+            ctx.collect(tb)
+        assert ei.value.result.first_bad == 777
+        assert_same(ctx.collect(tg), want)              # the neighbour in flight is untouched
+        assert_same(ctx.collect(ctx.submit(good)), want)   # and the failed batch's set is usable again
+    finally:
+        ctx.set_option("async", 0)
+
+
+def test_timing_events_only_on_every_kth_batch(ctx):
+    """"time_every" = K: per-kernel CUDA events on every K-th batch; the others report 0 and are still correct."""
+    batch = synth.generate("config2", n=4000, start=3)
+    want = oracle.register_batch(batch)
+    ctx.set_option("time_every", 3)
+    try:
+        timed = 0
+        for _ in range(6):
+            got = ctx.register_batch(batch)
+            assert_same(got, want)
+            timed += 1 if got.kernel_ms > 0 else 0
+        assert timed == 2
+    finally:
+        ctx.set_option("time_every", 1)
+    assert ctx.register_batch(batch).kernel_ms > 0
+
+
 def test_pipelined_variable_hostnames_alias_and_halves(small_chunks):
     recs = [{"domain": b"a%d.b%d.c" % (i, i % 7), "hostname": b"h" * (1 + i % 40), "type": b"host",
              "address": b"10.0.%d.%d" % (i % 200, i % 250), "ttl": [None, 30, 86400][i % 3],
