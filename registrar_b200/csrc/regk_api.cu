@@ -78,6 +78,9 @@ struct regk_ctx {
     const uint8_t *last_path_bytes = nullptr;
     const unsigned long long *last_path_off = nullptr;
     uint64_t last_n = 0;
+    const uint32_t *last_host_off = nullptr;
+    uint32_t last_host_stride = 0;
+    bool last_alias = false;
     DevBuf par_len, par_slot, par_table, par_totals, par_unique;
     HostBuf h_par_len, h_par_unique, h_par_count;
     std::vector<cudaEvent_t> pipe_events;
@@ -108,6 +111,9 @@ struct regk_ctx {
         bool timed = true;                      /* ev[0..2] were recorded for this batch */
         const uint8_t *dev_path_bytes = nullptr;        /* where this batch's path stream lives on the device */
         const unsigned long long *dev_path_off = nullptr;
+        const uint32_t *dev_host_off = nullptr;         /* how its paths end: hostname lengths (NULL: fixed stride) */
+        uint32_t host_stride = 0;
+        bool alias = false;
         bool in_use = false;
         uint64_t n = 0;
         uint32_t flags = 0;
@@ -1078,6 +1084,9 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             ctx->last_path_bytes = do_path ? pp.out_bytes : nullptr;
             ctx->last_path_off = do_path ? pp.out_off : nullptr;
             ctx->last_n = do_path ? n : 0;
+            ctx->last_host_off = pp.host_off;
+            ctx->last_host_stride = pp.host_stride;
+            ctx->last_alias = alias;
         }
         if (rc != REGK_ERR_STATE + 100)         /* anything but "needs the exact redo" */
             return rc;
@@ -1093,6 +1102,9 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     slot.d_status = d_status;
     slot.dev_path_bytes = (n && do_path) ? pp.out_bytes : nullptr;
     slot.dev_path_off = (n && do_path) ? pp.out_off : nullptr;
+    slot.dev_host_off = pp.host_off;
+    slot.host_stride = pp.host_stride;
+    slot.alias = alias;
     const bool fused_len = n && do_path && do_json;
     /* per-kernel timing events sit between the launches and cost a few microseconds of stream gaps per batch:
        "time_every" = K keeps them on every K-th batch only (the others report kernel times of 0) */
@@ -1231,6 +1243,9 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     ctx->last_path_bytes = st.bad_bits ? nullptr : slot->dev_path_bytes;
     ctx->last_path_off = st.bad_bits ? nullptr : slot->dev_path_off;
     ctx->last_n = (st.bad_bits || !slot->dev_path_off) ? 0 : n;
+    ctx->last_host_off = slot->dev_host_off;
+    ctx->last_host_stride = slot->host_stride;
+    ctx->last_alias = slot->alias;
     float ms_p = 0, ms_jl = 0, ms_j = 0;
     if (slot->timed) {
         cudaEventElapsedTime(&ms_p, slot->ev[0], slot->ev[1]);
@@ -1345,6 +1360,9 @@ int regk_parent_dirs(regk_ctx *ctx, uint32_t flags, regk_parents *out)
     p.super_total = (unsigned long long *)((uint8_t *)ctx->par_totals.p + ((ntiles * 4 + 15) & ~(size_t)15));
     p.unique_first = (unsigned long long *)ctx->par_unique.p;
     p.n_unique = p.unique_first + n;
+    p.tail_mode = ctx->last_alias ? 0u : (ctx->last_host_off ? 2u : 1u);
+    p.host_stride = ctx->last_host_stride;
+    p.host_off = ctx->last_host_off;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));

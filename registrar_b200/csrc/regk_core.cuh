@@ -1095,5 +1095,75 @@ RG_HD void emit_json(const FSrc &blob, const TypeFrag &tf, const uint32_t (&aw)[
     }
 }
 
+/* ------------------------------------ setupDirectories (regk_parents.cuh) -- */
+
+/* node (>= 6) posix path.dirname of an absolute path of n >= 1 bytes, as the length of the directory prefix:
+   trailing slashes are skipped, the directory ends before the last '/' that precedes the final segment;
+   '/' when there is none, '//' when that separator sits at index 1 (reference lib/register.js:118). */
+RG_HD uint32_t dirname_len_scan(const uint8_t *p, uint32_t n)
+{
+    bool matched_slash = true;
+    for (uint32_t i = n - 1; i >= 1; --i) {
+        if (p[i] == '/') {
+            if (!matched_slash)
+                return i == 1 ? 2u : i;
+        } else {
+            matched_slash = false;
+        }
+    }
+    return 1;
+}
+
+/* The same for a host node whose last segment is a hostname of H bytes (non-empty, no '/': the fence): the
+   separator in front of it is the one dirname stops at, so no scan is needed. */
+RG_HD uint32_t dirname_len_host(uint32_t n, uint32_t H)
+{
+    const uint32_t d = n - H - 1u;
+    return d ? d : 1u;
+}
+
+/* k-th 4-byte group of the byte string that starts at byte `o` of the word array W (readable one word past it) */
+RG_HD uint32_t string_word(const uint32_t *W, uint64_t o, uint32_t k)
+{
+    const uint64_t b = (o >> 2) + k;
+    return funnel_r(W[b], W[b + 1], ((uint32_t)o & 3u) * 8u);
+}
+
+/* 32-bit hash of the n bytes at byte offset o (murmur3 mixing, word-wise; only picks a table slot) */
+RG_HD uint32_t string_hash32(const uint32_t *W, uint64_t o, uint32_t n)
+{
+    uint32_t h = 0x9747B28Cu ^ n;
+    const uint32_t nw = n >> 2, rem = n & 3u;
+    for (uint32_t k = 0; k < nw + (rem ? 1u : 0u); k++) {
+        uint32_t w = string_word(W, o, k);
+        if (k == nw)
+            w &= low_bytes(rem);
+        w *= 0xCC9E2D51u;
+        w = (w << 15) | (w >> 17);
+        w *= 0x1B873593u;
+        h ^= w;
+        h = (h << 13) | (h >> 19);
+        h = h * 5u + 0xE6546B64u;
+    }
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+
+/* do the n bytes at byte offsets a and b of W agree? */
+RG_HD bool string_equal(const uint32_t *W, uint64_t a, uint64_t b, uint32_t n)
+{
+    const uint32_t nw = n >> 2, rem = n & 3u;
+    for (uint32_t k = 0; k < nw; k++)
+        if (string_word(W, a, k) != string_word(W, b, k))
+            return false;
+    if (rem)
+        return ((string_word(W, a, nw) ^ string_word(W, b, nw)) & low_bytes(rem)) == 0u;
+    return true;
+}
+
 }  /* namespace regk */
 #endif /* REGK_CORE_CUH */

@@ -10,8 +10,9 @@
  *   unique_first[]  the record index of the first occurrence of every distinct directory, ascending -
  *                   the exact set a batched mkdirp needs, byte-compared (hashing only picks the slot).
  *
- * Kernels: (1) regk_parent_kernel - one thread per record: backward scan for the directory length, 64-bit
- * hash of the prefix, insert into an open-addressing table whose slots hold "owner record + 1" (claimed by
+ * Kernels: (1) regk_parent_kernel - one thread per record: the directory length (host nodes: the path minus
+ * its hostname and separator, no scan; alias nodes: backward scan), a word-wise 32-bit hash of the prefix
+ * (composers in regk_core.cuh, emulated on the CPU by tests/emul), insert into an open-addressing table whose slots hold "owner record + 1" (claimed by
  * one atomicCAS, so the owner is stable the moment it is visible); a record that meets a claimed slot
  * compares its prefix with the owner's bytes - equal: same directory (atomicMin of the first index),
  * different: next slot.  (2) regk_parent_mark_kernel - a record is a first occurrence iff the table says
@@ -38,42 +39,22 @@ struct ParentParams {
     unsigned long long *super_total;            /* [ntiles / SUPER + 1] */
     unsigned long long *unique_first;           /* out: ascending record indices */
     unsigned long long *n_unique;               /* out */
+    /* how the last segment is known: 0 = scan the path (alias nodes), 1 = every path ends in a hostname of
+       host_stride bytes, 2 = ... of host_off[i + 1] - host_off[i] bytes (the batch's own input array) */
+    uint32_t tail_mode, host_stride;
+    const uint32_t *host_off;
 };
 
-/* node (>= 6) posix path.dirname on an absolute path of n >= 1 bytes: the length of the directory prefix */
-__device__ __forceinline__ uint32_t dirname_len(const uint8_t *p, uint32_t n)
+/* length of path.dirname(path_i) for record i whose path is the n bytes at `mine` */
+__device__ __forceinline__ uint32_t parent_length(const ParentParams &p, uint64_t i, const uint8_t *mine, uint32_t n)
 {
-    bool matched_slash = true;
-    for (uint32_t i = n - 1; i >= 1; --i) {
-        if (p[i] == '/') {
-            if (!matched_slash)
-                return i == 1 ? 2u : i;                     /* '//' when the separator sits at index 1 */
-        } else {
-            matched_slash = false;
-        }
-    }
-    return 1;                                               /* no separator beyond the root: '/' */
-}
-
-__device__ __forceinline__ unsigned long long hash_bytes(const uint8_t *p, uint32_t n)
-{
-    unsigned long long h = 0x9E3779B97F4A7C15ull ^ n;
-    for (uint32_t i = 0; i < n; i++) {
-        h ^= p[i];
-        h *= 0x100000001B3ull;                              /* FNV-1a step */
-    }
-    h ^= h >> 32;
-    h *= 0xD6E8FEB86659FD93ull;
-    h ^= h >> 32;
-    return h;
-}
-
-__device__ __forceinline__ bool same_bytes(const uint8_t *a, const uint8_t *b, uint32_t n)
-{
-    for (uint32_t i = 0; i < n; i++)
-        if (a[i] != b[i])
-            return false;
-    return true;
+    if (n == 0)
+        return 0;
+    if (p.tail_mode == 1u)
+        return dirname_len_host(n, p.host_stride);
+    if (p.tail_mode == 2u)
+        return dirname_len_host(n, p.host_off[i + 1] - p.host_off[i]);
+    return dirname_len_scan(mine, n);
 }
 
 __global__ void __launch_bounds__(256) regk_parent_kernel(const ParentParams p)
@@ -82,11 +63,10 @@ __global__ void __launch_bounds__(256) regk_parent_kernel(const ParentParams p)
     if (i >= p.n)
         return;
     const unsigned long long o0 = p.path_off[i], o1 = p.path_off[i + 1];
-    const uint8_t *mine = p.path_bytes + o0;
-    const uint32_t len = (uint32_t)(o1 - o0);
-    const uint32_t plen = len ? dirname_len(mine, len) : 0u;
+    const uint32_t *W = reinterpret_cast<const uint32_t *>(p.path_bytes);
+    const uint32_t plen = parent_length(p, i, p.path_bytes + o0, (uint32_t)(o1 - o0));
     p.parent_len[i] = plen;
-    uint32_t slot = (uint32_t)hash_bytes(mine, plen) & p.mask;
+    uint32_t slot = string_hash32(W, o0, plen) & p.mask;
     for (;;) {
         uint32_t cur = p.owner[slot];
         if (cur == 0u) {
@@ -99,10 +79,8 @@ __global__ void __launch_bounds__(256) regk_parent_kernel(const ParentParams p)
             break;
         /* compare with the owner's directory, derived from its own path (its parent_len may not be stored yet) */
         const unsigned long long q0 = p.path_off[j], q1 = p.path_off[j + 1];
-        const uint8_t *theirs = p.path_bytes + q0;
-        const uint32_t tlen = (uint32_t)(q1 - q0);
-        const uint32_t tpl = tlen ? dirname_len(theirs, tlen) : 0u;
-        if (tpl == plen && same_bytes(mine, theirs, plen))
+        const uint32_t tpl = parent_length(p, j, p.path_bytes + q0, (uint32_t)(q1 - q0));
+        if (tpl == plen && string_equal(W, o0, q0, plen))
             break;                                          /* same directory */
         slot = (slot + 1u) & p.mask;
     }

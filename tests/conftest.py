@@ -41,6 +41,7 @@ def emul(built):
     for f in ("emul_paths", "emul_jsons", "emul_dec", "emul_ndigits"):
         getattr(lib, f).restype = C.c_uint32
     lib.emul_build_blob.restype = C.c_int
+    lib.emul_parents.restype = C.c_uint64
     return lib
 
 

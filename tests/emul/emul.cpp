@@ -273,6 +273,52 @@ uint32_t emul_ndigits(uint32_t v)
     return ndigits_u32(v);
 }
 
+/* setupDirectories pass (regk_parents.cuh) run serially with the same helpers: directory lengths, table
+   insertion with byte-exact comparison, first occurrences in record order.  `path_words` must be readable one
+   word past the stream.  tail_mode as in ParentParams.  Returns the number of distinct directories. */
+uint64_t emul_parents(const uint32_t *path_words, const uint64_t *path_off, uint64_t n, uint32_t tail_mode,
+    uint32_t host_stride, const uint32_t *host_off, uint32_t *parent_len, uint64_t *unique_first)
+{
+    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(path_words);
+    uint64_t slots = 16;                                        /* small on purpose: probing gets exercised */
+    while (slots < 2 * n)
+        slots <<= 1;
+    std::vector<uint32_t> owner(slots, 0), first(slots, 0xFFFFFFFFu), slot_of(n);
+    auto plen_of = [&](uint64_t i) -> uint32_t {
+        const uint32_t len = (uint32_t)(path_off[i + 1] - path_off[i]);
+        if (len == 0)
+            return 0;
+        if (tail_mode == 1)
+            return dirname_len_host(len, host_stride);
+        if (tail_mode == 2)
+            return dirname_len_host(len, host_off[i + 1] - host_off[i]);
+        return dirname_len_scan(bytes + path_off[i], len);
+    };
+    for (uint64_t i = 0; i < n; i++) {
+        const uint32_t plen = plen_of(i);
+        parent_len[i] = plen;
+        uint32_t slot = string_hash32(path_words, path_off[i], plen) & (uint32_t)(slots - 1);
+        for (;;) {
+            if (owner[slot] == 0) {
+                owner[slot] = (uint32_t)i + 1;
+                break;
+            }
+            const uint64_t j = owner[slot] - 1;
+            if (plen_of(j) == plen && string_equal(path_words, path_off[i], path_off[j], plen))
+                break;
+            slot = (slot + 1) & (uint32_t)(slots - 1);
+        }
+        slot_of[i] = slot;
+        if (first[slot] > (uint32_t)i)
+            first[slot] = (uint32_t)i;
+    }
+    uint64_t nu = 0;
+    for (uint64_t i = 0; i < n; i++)
+        if (first[slot_of[i]] == (uint32_t)i)
+            unique_first[nu++] = i;
+    return nu;
+}
+
 }  /* extern "C" */
 
 #include "../../registrar_b200/csrc/regk_types.hpp"

@@ -171,6 +171,47 @@ def test_port_lists_at_every_byte_phase(emul, generic):
     check_equal(*run_emul(emul, RecordBatch.from_records(recs), generic))
 
 
+def _emul_parents(emul, batch, want):
+    n = batch.n
+    words = np.zeros((int(want.path_off[-1]) + 11) // 4 + 2, np.uint32)
+    words.view(np.uint8)[:int(want.path_off[-1])] = want.path_bytes
+    mode = 0 if batch.alias else (2 if batch.host_off is not None else 1)
+    plen = np.zeros(n, np.uint32)
+    uniq = np.zeros(n + 1, np.uint64)
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    off = np.ascontiguousarray(want.path_off, dtype=np.uint64)
+    emul.emul_parents.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]
+    nu = emul.emul_parents(vp(words), vp(off), n, mode, int(batch.host_stride or 0), vp(batch.host_off), vp(plen), vp(uniq))
+    return plen, uniq[:nu]
+
+
+@pytest.mark.parametrize("alias", [False, True])
+def test_parent_dirs_helpers(emul, alias):
+    """dirname lengths, word-wise hash/compare and first-occurrence dedup of regk_parents.cuh, run serially on the
+    CPU with the same helpers, against oracle.parent_dirs (itself pinned by the reference's mkdirp arguments)."""
+    rng = np.random.default_rng(7)
+    batches = []
+    # few directories, many instances; variable and fixed hostname lengths; every alignment of the prefix
+    for var in (False, True):
+        recs = [{"domain": b"svc%d.dc%d.example.com" % (i % 13, i % 3),
+                 "hostname": (b"h" * (1 + i % 9)) if var else b"%08x" % i, "type": b"host", "address": b"1.1.1.1"}
+                for i in range(700)]
+        batches.append(RecordBatch.from_records(recs, alias=alias))
+    batches.append(RecordBatch.from_records(
+        [{"domain": d, "hostname": b"h%d" % (i % 2), "type": b"host", "address": b"1.1.1.1"}
+         for i, d in enumerate(EDGE_DOMAINS * 3)], alias=alias))
+    b3 = synth.generate("config3", n=3000, start=5)
+    batches.append(b3 if not alias else RecordBatch.from_records([b3.record(i) for i in range(600)], alias=True))
+    for batch in batches:
+        want = oracle.register_batch(batch)
+        assert want.bad_bits == 0
+        wlen, wfirst = oracle.parent_dirs(want)
+        plen, firsts = _emul_parents(emul, batch, want)
+        assert np.array_equal(plen, wlen)
+        assert np.array_equal(firsts, wfirst)
+
+
 def test_decimal(emul):
     out = (C.c_uint8 * 16)()
     vals = list(range(0, 12000)) + [99999, 100000, 655350, 9999999, 10000000, 99999999, 100000000, 123456789,

@@ -425,7 +425,7 @@ def test_async_host_batch_outside_the_fence_fails_alone(ctx):
     recs = [{"domain": b"svc%d.example.com" % i, "hostname": b"h", "type": b"host", "address": b"10.0.0.1"}
             for i in range(2000)]
     recs[777]["hostname"] = b"a/b"
-    bad = RecordBatch.from_records(recs)
+    bad = RecordBatch.from_records(recs, types=good.types)       # one type table for both: it cannot change in flight
     want = oracle.register_batch(good)
     ctx.set_option("async", 1)
     try:
