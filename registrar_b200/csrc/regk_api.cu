@@ -82,6 +82,7 @@ struct regk_ctx {
     uint32_t last_host_stride = 0;
     bool last_alias = false;
     DevBuf par_len, par_slot, par_table, par_totals, par_unique;
+    cudaEvent_t par_ev[2] = {nullptr, nullptr};
     HostBuf h_par_len, h_par_unique, h_par_count;
     std::vector<cudaEvent_t> pipe_events;
     /* workspace: DevStatus | two-level byte totals of both halves (stream-ordered reuse; host pipelining) */
@@ -579,6 +580,9 @@ void regk_destroy(regk_ctx *ctx)
     for (DevBuf *b : {&ctx->par_len, &ctx->par_slot, &ctx->par_table, &ctx->par_totals, &ctx->par_unique})
         if (b->p)
             cudaFree(b->p);
+    for (auto &ev : ctx->par_ev)
+        if (ev)
+            cudaEventDestroy(ev);
     for (HostBuf *b : {&ctx->h_par_len, &ctx->h_par_unique, &ctx->h_par_count})
         if (b->p)
             cudaFreeHost(b->p);
@@ -1363,9 +1367,11 @@ int regk_parent_dirs(regk_ctx *ctx, uint32_t flags, regk_parents *out)
     p.tail_mode = ctx->last_alias ? 0u : (ctx->last_host_off ? 2u : 1u);
     p.host_stride = ctx->last_host_stride;
     p.host_off = ctx->last_host_off;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
+    if (!ctx->par_ev[0]) {
+        CK(cudaEventCreate(&ctx->par_ev[0]));
+        CK(cudaEventCreate(&ctx->par_ev[1]));
+    }
+    cudaEvent_t e0 = ctx->par_ev[0], e1 = ctx->par_ev[1];
     CK(cudaMemsetAsync(p.owner, 0, slots * 4, s));
     CK(cudaMemsetAsync(p.first, 0xFF, slots * 4, s));
     CK(cudaMemsetAsync(ctx->par_totals.p, 0, totals_bytes, s));
@@ -1378,9 +1384,8 @@ int regk_parent_dirs(regk_ctx *ctx, uint32_t flags, regk_parents *out)
     CK(cudaMemcpyAsync(ctx->h_par_count.p, p.n_unique, 8, cudaMemcpyDeviceToHost, s));
     cudaError_t e = cudaStreamSynchronize(s);
     float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    if (e == cudaSuccess)
+        cudaEventElapsedTime(&ms, e0, e1);
     if (e != cudaSuccess)
         return fail(ctx, REGK_ERR_CUDA, "regk_parent_dirs: kernel execution failed: %s", cudaGetErrorString(e));
     const uint64_t nu = *(const unsigned long long *)ctx->h_par_count.p;
