@@ -354,6 +354,28 @@ def test_parent_dirs_edge_paths(ctx):
     assert got.path(doms.index(b""))[:int(plen[doms.index(b"")])] == b"/"
 
 
+def test_parent_dirs_after_chunked_and_async_host_batches(small_chunks):
+    """the pass finds the device copy of the path stream whichever way the batch travelled: chunk-pipelined
+    synchronous call, or one of the two alternating sets of an async submit/collect"""
+    ctx = small_chunks
+    a = synth.generate("config3", n=3000, start=100)            # chunk_records = 512: six chunks
+    b = synth.generate("config5", n=2500, start=200)
+    wa, wb = oracle.register_batch(a), oracle.register_batch(b)
+    got = ctx.register_batch(a)
+    assert got.launches >= 10
+    plen, firsts, _ = ctx.parent_dirs()
+    wl, wf = oracle.parent_dirs(wa)
+    assert np.array_equal(plen, wl) and np.array_equal(firsts, wf)
+    ctx.set_option("async", 1)
+    ta, tb = ctx.submit(a), ctx.submit(b)
+    ctx.collect(ta)
+    ctx.collect(tb)                                             # the batch finished last is b, in the second set
+    ctx.set_option("async", 0)
+    plen, firsts, _ = ctx.parent_dirs()
+    wl, wf = oracle.parent_dirs(wb)
+    assert np.array_equal(plen, wl) and np.array_equal(firsts, wf)
+
+
 def test_parent_dirs_needs_a_finished_path_batch(ctx):
     from registrar_b200._native import RegkError
     batch = synth.generate("config1")
