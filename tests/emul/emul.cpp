@@ -21,7 +21,7 @@
 using namespace regk;
 
 namespace {
-constexpr uint32_t TILE = 256;
+constexpr uint32_t TILE = 128;          /* as REGK_TILE in regk_kernels.cuh */
 
 struct Frags {
     std::vector<uint8_t> blob;
