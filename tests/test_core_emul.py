@@ -273,5 +273,9 @@ def test_hypothesis_records(emul):
         batch = RecordBatch.from_records(recs, alias=alias)
         for generic in (0, 1):
             check_equal(*run_emul(emul, batch, generic))
+        want = oracle.register_batch(batch)                      # and the parent-directory pass on the same paths
+        wlen, wfirst = oracle.parent_dirs(want)
+        plen, firsts = _emul_parents(emul, batch, want)
+        assert np.array_equal(plen, wlen) and np.array_equal(firsts, wfirst)
 
     inner()
