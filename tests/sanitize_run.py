@@ -1,4 +1,6 @@
-"""Small end-to-end run for compute-sanitizer (memcheck / racecheck): every kernel path once."""
+"""TEST INFRASTRUCTURE: small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck), every kernel
+path once, each result compared with the oracle.  Run on the GPU box:
+    compute-sanitizer --tool memcheck python tests/sanitize_run.py"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
