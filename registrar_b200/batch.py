@@ -43,6 +43,16 @@ def _pack(strings: Sequence[bytes]):
     return data, off
 
 
+def _integral(v, lo: int, hi: int, what: str) -> int:
+    """Numbers outside the kernels' domain are an error, never a silently different payload: the reference
+    prints any JS number (ttl 1.5 -> "ttl":1.5, lib/register.js:144), the kernels print int32 / uint32."""
+    if isinstance(v, bool) or not isinstance(v, (int, float, np.integer, np.floating)) or v != int(v):
+        raise ValueError("%s %r is outside the supported input domain (integers only)" % (what, v))
+    if not lo <= int(v) <= hi:
+        raise ValueError("%s %r is outside the supported input domain [%d, %d]" % (what, v, lo, hi))
+    return int(v)
+
+
 def _b(x) -> bytes:
     return x if isinstance(x, (bytes, bytearray)) else str(x).encode("utf-8")
 
@@ -89,10 +99,10 @@ class RecordBatch:
                 tlist.append(t)
             tids.append(tindex[t])
             ttl = r.get("ttl")
-            ttls.append(TTL_ABSENT if ttl is None else int(ttl))
+            ttls.append(TTL_ABSENT if ttl is None else _integral(ttl, TTL_ABSENT + 1, 2 ** 31 - 1, "ttl"))
             p = r.get("ports")
             present.append(0 if p is None else 1)
-            plist.append([] if p is None else [int(x) for x in p])
+            plist.append([] if p is None else [_integral(x, 0, 2 ** 32 - 1, "port") for x in p])
         if len(tlist) > 255:
             raise ValueError("at most 255 record types per batch")
         n = len(records)

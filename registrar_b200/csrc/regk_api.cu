@@ -235,6 +235,30 @@ struct HostPipe {
     void *dev[11] = {};
 };
 
+/* run_pipelined uses the caller's offsets at chunk boundaries as cudaMemcpyAsync byte ranges: every boundary
+   must be monotone and inside the declared array (off[n]).  A batch that fails this takes the unpipelined path,
+   whose kernels report the first offending record as REGK_BAD_TOO_LARGE without dereferencing anything. */
+static bool chunk_bounds_ok(const regk_batch *b, uint64_t chunk, bool do_path, bool do_json, bool alias)
+{
+    const uint64_t n = b->n;
+    auto ok = [&](const uint32_t *off) {
+        if (!off)
+            return true;
+        uint32_t prev = off[0];
+        const uint32_t last = off[n];
+        if (prev != 0 && prev > last)
+            return false;
+        for (uint64_t r = chunk; r < n; r += chunk) {
+            if (off[r] < prev || off[r] > last)
+                return false;
+            prev = off[r];
+        }
+        return true;
+    };
+    return (!do_path || (ok(b->domain_off) && (alias || ok(b->host_off)))) &&
+           (!do_json || (ok(b->addr_off) && ok(b->ports_off)));
+}
+
 static int run_pipelined(regk_ctx *ctx, const regk_batch *b, regk_result *res, const PathParams &pp0, size_t path_smem,
     const JsonParams &jp0, size_t json_smem, const HostPipe &hp)
 {
@@ -869,7 +893,7 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     /* Host buffers in and out, large batch: overlap H2D, kernels and D2H chunk by chunk (run_pipelined). */
     const uint64_t chunk_records = (uint64_t)opt_get(ctx, "chunk_records", 262144) / TILE * TILE;
     const bool pipelined = !in_dev && !out_dev && !async && chunk_records && n >= 2 * chunk_records &&
-        !opt_get(ctx, "force_generic", 0);
+        !opt_get(ctx, "force_generic", 0) && chunk_bounds_ok(b, chunk_records, do_path, do_json, alias);
     /* Host buffers in and out with the "async" option: two batches may be in flight, each in its own HostSet. */
     regk_ctx::HostSet *hs = (!in_dev && !out_dev && async && n) ? &ctx->hset[ctx->hseq & 1] : nullptr;
     if (hs) {

@@ -80,9 +80,10 @@ inline int build_type_blob(const std::vector<std::string> &types, std::vector<ui
     for (size_t i = 0; i < ntypes; i++) {
         const std::string &t = types[i];
         /* lib/register.js:152 `_obj[type] = {...}`: these names would overwrite a fixed key in place, and
-           array-index names are enumerated first by V8 — both change the byte layout. */
-        if (t == "type" || t == "address" || t == "ttl" || is_array_index(t)) {
-            *err = "type '" + t + "' collides with a fixed key or is an array index";
+           array-index names are enumerated first by V8 — both change the byte layout.  "__proto__" assigns the
+           object's prototype instead of creating an own property, so JSON.stringify drops the nested object. */
+        if (t == "type" || t == "address" || t == "ttl" || t == "__proto__" || is_array_index(t)) {
+            *err = "type '" + t + "' collides with a fixed key, is an array index or is __proto__";
             return 1;
         }
         const std::string q = json_escape(t);

@@ -39,6 +39,14 @@ function toBatch(records, types, flags) {
         present = Buffer.alloc(n), flat = [];
     records.forEach(function (r, i) {
         typeId[i] = types.indexOf(r.type);
+        /* out-of-domain numbers are an error, never a silently different payload: the kernels print integers,
+           the reference prints any JS number (1.5, 1e21 ...) */
+        if (r.ttl !== undefined && (!Number.isInteger(r.ttl) || r.ttl <= TTL_ABSENT || r.ttl > 2147483647))
+            throw (new RangeError('record ' + i + ': ttl ' + r.ttl + ' is outside the supported domain (int32)'));
+        (r.ports || []).forEach(function (p) {
+            if (!Number.isInteger(p) || p < 0 || p > 4294967295)
+                throw (new RangeError('record ' + i + ': port ' + p + ' is outside the supported domain (uint32)'));
+        });
         ttl.writeInt32LE(r.ttl === undefined ? TTL_ABSENT : r.ttl, 4 * i);
         if (r.ports) { present[i] = 1; flat = flat.concat(r.ports); }
         portsOff.writeUInt32LE(flat.length, 4 * (i + 1));
@@ -68,30 +76,51 @@ function registerBatch(records, cb) {
     });
 }
 
-function register(opts, cb) {
-    /* argument contract: lib/register.js:175-201, verbatim semantics */
-    assert.object(opts, 'options');
-    assert.object(opts.log, 'options.log');
-    assert.optionalString(opts.adminIp, 'options.adminIp');
-    assert.optionalObject(opts.aliases, 'options.aliases');
-    assert.string(opts.domain, 'options.domain');
-    assert.object(opts.registration, 'options.registration');
-    assert.string(opts.registration.type, 'options.registration.type');
-    assert.optionalNumber(opts.registration.ttl, 'options.registration.ttl');
-    assert.optionalArrayOfNumber(opts.registration.ports, 'options.registration.ports');
-    assert.optionalObject(opts.registration.service, 'options.registration.service');
-    if (opts.registration.service) {
-        var s2 = opts.registration.service.service;
-        assert.ok(opts.registration.service.type === 'service');
-        assert.object(s2, 'options.registration.service.service');
-        assert.string(s2.srvce, 'options.registration.service.service.srvce');
-        assert.string(s2.proto, 'options.registration.service.service.proto');
-        assert.optionalNumber(s2.ttl, 'options.registration.service.service.ttl');
-        s2.ttl = s2.ttl !== undefined ? s2.ttl : 60;
-        assert.number(s2.port, 'options.registration.service.service.port');
-    }
-    assert.object(opts.zk, 'options.zk');
+/*
+ * The argument contract of register(opts, cb) — reference lib/register.js:175-201 — as data: one row per
+ * check, [assert-plus method, path below `options`, only-if path].  Rows run in order, so the first failing
+ * check raises the same AssertionError (same method, same label) as the reference does.  Two entries are not
+ * plain type checks and are handled by name: 'service.type === service' (register.js:189) and the ttl default
+ * (register.js:197), which the reference applies in the middle of the checks.
+ */
+var CONTRACT = [
+    [ 'object', '' ], [ 'object', 'log' ], [ 'optionalString', 'adminIp' ], [ 'optionalObject', 'aliases' ],
+    [ 'string', 'domain' ], [ 'object', 'registration' ], [ 'string', 'registration.type' ],
+    [ 'optionalNumber', 'registration.ttl' ], [ 'optionalArrayOfNumber', 'registration.ports' ],
+    [ 'optionalObject', 'registration.service' ],
+    [ 'string', 'registration.service.type', 'registration.service' ],
+    [ 'isServiceType', 'registration.service.type', 'registration.service' ],
+    [ 'object', 'registration.service.service', 'registration.service' ],
+    [ 'string', 'registration.service.service.srvce', 'registration.service' ],
+    [ 'string', 'registration.service.service.proto', 'registration.service' ],
+    [ 'optionalNumber', 'registration.service.service.ttl', 'registration.service' ],
+    [ 'defaultTtl60', 'registration.service.service', 'registration.service' ],
+    [ 'number', 'registration.service.service.port', 'registration.service' ],
+    [ 'object', 'zk' ]
+];
+
+function dig(root, dotted) {
+    return (dotted === '' ? root : dotted.split('.').reduce(function (o, k) { return (o[k]); }, root));
+}
+
+function checkContract(opts, cb) {
+    CONTRACT.forEach(function (row) {
+        var how = row[0], where = row[1], onlyIf = row[2];
+        if (onlyIf !== undefined && !dig(opts, onlyIf))
+            return;
+        var v = dig(opts, where), label = where === '' ? 'options' : 'options.' + where;
+        if (how === 'isServiceType')
+            assert.ok(v === 'service');
+        else if (how === 'defaultTtl60')
+            v.ttl = v.ttl !== undefined ? v.ttl : 60;
+        else
+            assert[how](v, label);
+    });
     assert.func(cb, 'callback');
+}
+
+function register(opts, cb) {
+    checkContract(opts, cb);
     cb = once(cb);
 
     var reg = opts.registration, zk = opts.zk, aliases = opts.aliases || [];

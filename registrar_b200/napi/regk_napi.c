@@ -8,8 +8,13 @@
  *                       addrBytes, addrOff, ttl, portsOff?, ports?, portsPresent?},  // Buffers over SoA arrays
  *                      function (err, res) { res.pathBytes, res.pathOff, res.jsonBytes, res.jsonOff, res.kernelMs });
  *
- * Threading: the context is single-owner; the batch runs on a libuv worker thread
- * (napi_async_work) and the errback fires on the main loop, like every callback in the reference.
+ * Threading: the context is single-owner, but libuv runs queued napi_async_work items on a POOL
+ * of worker threads, so two registerBatch() calls can execute at the same time.  Everything that touches the
+ * context therefore happens inside job_execute under one mutex: the job's own copy of the type table is
+ * installed if it differs from the one the context holds, the batch runs, and the results are copied out of
+ * the library's recycled pinned buffers into memory the job owns — all before the lock is released.  The main
+ * thread never calls into the context (setTypes only records the table for the jobs queued after it); the
+ * errback fires on the main loop, like every callback in the reference.
  *
  * Build (on a machine with Node.js; not possible in the image this repo is developed in — no node, no
  * node_api.h): node-gyp with `libraries: ['-lregk']`, or
@@ -21,12 +26,43 @@
 #else
 #include <node_api.h>
 #endif
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "../../include/regk.h"
 
 static regk_ctx *g_ctx;
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;     /* serialises every use of g_ctx (worker threads) */
+
+/* an immutable, reference-counted type table: setTypes() publishes one, every job pins the one current when
+   it is queued (main thread only touches g_types / refcounts under g_lock as well) */
+typedef struct {
+    int refs;
+    uint32_t n;
+    char **strs;
+    uint32_t *lens;
+} types_t;
+static types_t *g_types;            /* what setTypes() recorded last */
+static types_t *g_installed;        /* what the context holds (compared by identity) */
+
+static void types_unref(types_t *t)
+{
+    uint32_t i;
+    int dead;
+    if (!t)
+        return;
+    pthread_mutex_lock(&g_lock);
+    dead = --t->refs == 0;
+    pthread_mutex_unlock(&g_lock);
+    if (!dead)
+        return;
+    for (i = 0; i < t->n; i++)
+        free(t->strs[i]);
+    free(t->strs);
+    free(t->lens);
+    free(t);
+}
 
 static const void *buf_or_null(napi_env env, napi_value obj, const char *name, size_t *len)
 {
@@ -56,15 +92,57 @@ typedef struct {
     char error[512];
     napi_ref cb, keepalive;             /* the batch object: keeps the Buffers alive while the worker runs */
     napi_async_work work;
+    types_t *types;                     /* pinned at queue time */
+    /* the job's own copies of the results (made under the lock, handed to V8 as external buffers) */
+    uint8_t *path_bytes, *json_bytes;
+    uint64_t *path_off, *json_off;
 } job_t;
+
+static void *dup_bytes(const void *p, size_t n)
+{
+    void *q = malloc(n ? n : 1);
+    if (q && n)
+        memcpy(q, p, n);
+    return q;
+}
+
+static void free_hint(napi_env env, void *data, void *hint)
+{
+    (void)env;
+    (void)hint;
+    free(data);
+}
 
 static void job_execute(napi_env env, void *data)
 {
     job_t *j = (job_t *)data;
     (void)env;
-    j->status = regk_register_batch(g_ctx, &j->batch, &j->result);      /* host buffers in, pinned host buffers out */
-    if (j->status != REGK_OK)
+    pthread_mutex_lock(&g_lock);
+    j->status = REGK_OK;
+    if (j->types && j->types != g_installed) {
+        j->status = regk_set_types(g_ctx, (const char *const *)j->types->strs, j->types->lens, j->types->n);
+        if (j->status == REGK_OK)
+            g_installed = j->types;     /* identity only; the job's own reference keeps it alive while it matters */
+    }
+    if (j->status == REGK_OK)
+        j->status = regk_register_batch(g_ctx, &j->batch, &j->result);  /* host buffers in, pinned host buffers out */
+    if (j->status != REGK_OK) {
         strncpy(j->error, regk_last_error(g_ctx), sizeof j->error - 1);
+    } else {
+        const size_t noff = (size_t)(j->result.n + 1) * 8;
+        j->path_bytes = (uint8_t *)dup_bytes(j->result.path_bytes, (size_t)j->result.path_total);
+        j->json_bytes = (uint8_t *)dup_bytes(j->result.json_bytes, (size_t)j->result.json_total);
+        j->path_off = (uint64_t *)dup_bytes(j->result.path_off, noff);
+        j->json_off = (uint64_t *)dup_bytes(j->result.json_off, noff);
+        regk_release(g_ctx, &j->result);
+        if (!j->path_bytes || !j->json_bytes || !j->path_off || !j->json_off) {
+            j->status = REGK_ERR_NOMEM;
+            strncpy(j->error, "out of memory copying the results", sizeof j->error - 1);
+        }
+    }
+    if (g_installed == j->types && j->status != REGK_OK && j->types)
+        g_installed = NULL;             /* be conservative after a failure: the next job re-installs its table */
+    pthread_mutex_unlock(&g_lock);
 }
 
 static void job_complete(napi_env env, napi_status st, void *data)
@@ -89,21 +167,27 @@ static void job_complete(napi_env env, napi_status st, void *data)
         const uint64_t n = j->result.n;
         napi_get_null(env, &argv[0]);
         napi_create_object(env, &res);
-        /* copies out of the library's pinned buffers (they are recycled by the next batch) */
-        napi_create_buffer_copy(env, (size_t)j->result.path_total, j->result.path_bytes, NULL, &v);
+        /* the job's own copies (made under the lock in job_execute); V8 frees them with the Buffers */
+        napi_create_external_buffer(env, (size_t)j->result.path_total, j->path_bytes, free_hint, NULL, &v);
         napi_set_named_property(env, res, "pathBytes", v);
-        napi_create_buffer_copy(env, (size_t)(n + 1) * 8, j->result.path_off, NULL, &v);
+        napi_create_external_buffer(env, (size_t)(n + 1) * 8, j->path_off, free_hint, NULL, &v);
         napi_set_named_property(env, res, "pathOff", v);
-        napi_create_buffer_copy(env, (size_t)j->result.json_total, j->result.json_bytes, NULL, &v);
+        napi_create_external_buffer(env, (size_t)j->result.json_total, j->json_bytes, free_hint, NULL, &v);
         napi_set_named_property(env, res, "jsonBytes", v);
-        napi_create_buffer_copy(env, (size_t)(n + 1) * 8, j->result.json_off, NULL, &v);
+        napi_create_external_buffer(env, (size_t)(n + 1) * 8, j->json_off, free_hint, NULL, &v);
         napi_set_named_property(env, res, "jsonOff", v);
+        j->path_bytes = j->json_bytes = NULL;
+        j->path_off = j->json_off = NULL;
         napi_create_double(env, (double)j->result.kernel_ms, &v);
         napi_set_named_property(env, res, "kernelMs", v);
         argv[1] = res;
-        regk_release(g_ctx, &j->result);
         napi_call_function(env, undef, cb, 2, argv, NULL);
     }
+    free(j->path_bytes);
+    free(j->json_bytes);
+    free(j->path_off);
+    free(j->json_off);
+    types_unref(j->types);
     napi_delete_reference(env, j->cb);
     napi_delete_reference(env, j->keepalive);
     napi_delete_async_work(env, j->work);
@@ -135,6 +219,11 @@ static napi_value register_batch(napi_env env, napi_callback_info info)
     j->batch.ports_off = (const uint32_t *)buf_or_null(env, argv[0], "portsOff", NULL);
     j->batch.ports = (const uint32_t *)buf_or_null(env, argv[0], "ports", NULL);
     j->batch.ports_present = (const uint8_t *)buf_or_null(env, argv[0], "portsPresent", NULL);
+    pthread_mutex_lock(&g_lock);
+    j->types = g_types;
+    if (j->types)
+        j->types->refs++;
+    pthread_mutex_unlock(&g_lock);
     napi_create_reference(env, argv[0], 1, &j->keepalive);
     napi_create_reference(env, argv[1], 1, &j->cb);
     napi_create_string_utf8(env, "regk_register_batch", 19, &name);
@@ -145,31 +234,35 @@ static napi_value register_batch(napi_env env, napi_callback_info info)
 
 static napi_value set_types(napi_env env, napi_callback_info info)
 {
+    /* Main thread: only RECORDS the table.  It reaches the context inside the next job's job_execute, under
+       the lock, so a batch already running on a worker keeps the table it was queued with. */
     size_t argc = 1;
     napi_value argv[1], el;
     uint32_t n = 0, i;
-    char **strs;
-    uint32_t *lens;
-    int rc;
+    types_t *t, *old;
     napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
-    napi_get_array_length(env, argv[0], &n);
-    strs = (char **)calloc(n ? n : 1, sizeof *strs);
-    lens = (uint32_t *)calloc(n ? n : 1, sizeof *lens);
+    if (argc < 1 || napi_get_array_length(env, argv[0], &n) != napi_ok) {
+        napi_throw_error(env, NULL, "setTypes(types): an array of strings is required");
+        return NULL;
+    }
+    t = (types_t *)calloc(1, sizeof *t);
+    t->refs = 1;
+    t->n = n;
+    t->strs = (char **)calloc(n ? n : 1, sizeof *t->strs);
+    t->lens = (uint32_t *)calloc(n ? n : 1, sizeof *t->lens);
     for (i = 0; i < n; i++) {
         size_t l = 0;
         napi_get_element(env, argv[0], i, &el);
         napi_get_value_string_utf8(env, el, NULL, 0, &l);
-        strs[i] = (char *)malloc(l + 1);
-        napi_get_value_string_utf8(env, el, strs[i], l + 1, &l);
-        lens[i] = (uint32_t)l;
+        t->strs[i] = (char *)malloc(l + 1);
+        napi_get_value_string_utf8(env, el, t->strs[i], l + 1, &l);
+        t->lens[i] = (uint32_t)l;
     }
-    rc = regk_set_types(g_ctx, (const char *const *)strs, lens, n);
-    for (i = 0; i < n; i++)
-        free(strs[i]);
-    free(strs);
-    free(lens);
-    if (rc != REGK_OK)
-        napi_throw_error(env, NULL, regk_last_error(g_ctx));
+    pthread_mutex_lock(&g_lock);
+    old = g_types;
+    g_types = t;
+    pthread_mutex_unlock(&g_lock);
+    types_unref(old);
     return NULL;
 }
 

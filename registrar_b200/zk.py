@@ -16,7 +16,8 @@ from .registration import _a_func, _a_object, _a_array_of_string, _get, for_each
 
 def heartbeat(opts, cb: Callable, _timer=None):
     """lib/zk.js:21-44: stat() all nodes in parallel; on failure retry with exponential backoff
-    (initialDelay 1000 ms doubling up to maxDelay 30000 ms), failing after maxAttempts (5) attempts."""
+    (initialDelay 1000 ms doubling up to maxDelay 30000 ms).  backoff 2.x `failAfter(N)` (lib/zk.js:37) allows N
+    backoffs, i.e. N RETRIES after the first call: check() runs at most N + 1 times (default N = 5 -> 6 calls)."""
     _a_object(opts, "options")
     _a_array_of_string(_get(opts, "nodes"), "options.nodes")
     retry = _get(opts, "retry")
@@ -39,7 +40,7 @@ def heartbeat(opts, cb: Callable, _timer=None):
         def done(err=None):
             if not err:
                 cb(None)
-            elif state["attempt"] >= max_attempts:
+            elif state["attempt"] > max_attempts:          # max_attempts retries after the first call
                 cb(err)
             else:
                 d = state["delay"]

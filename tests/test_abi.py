@@ -65,3 +65,35 @@ def test_struct_layouts_match_header(built):
            C.sizeof(_native.CGather), _native.CGather.totals.offset, _native.CGather.json_off.offset,
            _native.CGather.json_cap.offset]
     assert [int(x) for x in out] == got
+
+
+def test_napi_shim_compiles():
+    """The N-API addon cannot be built here (no Node headers): compile it against the hand-declared
+    prototypes so that it cannot drift unnoticed (it had)."""
+    import subprocess
+    src = os.path.join(ROOT, "registrar_b200", "napi", "regk_napi.c")
+    subprocess.check_call(["gcc", "-std=c99", "-DREGK_NAPI_MIN_DECLS", "-fsyntax-only", "-Wall", "-Wextra", "-Werror",
+                           "-pthread", src])
+    text = open(src).read()
+    # every use of the context sits under the lock in job_execute (ADVICE r1): no regk_* call on the main thread
+    # except regk_create in init()
+    body = text[text.index("static napi_value set_types("):text.index("static napi_value init_ctx(")]
+    assert "regk_set_types(" not in body and "g_ctx" not in body
+
+
+def test_js_contract_table_matches_the_reference_asserts():
+    """napi/index.js validates register()'s arguments from a table; the rows must name the same checks, in the
+    same order, as the reference's assert block (lib/register.js:175-201) - compared against the list below,
+    which was transcribed from the reference and is also what registration.py enforces."""
+    js = open(os.path.join(ROOT, "registrar_b200", "napi", "index.js")).read()
+    table = js[js.index("var CONTRACT = ["):js.index("];", js.index("var CONTRACT = ["))]
+    rows = re.findall(r"\[ '([A-Za-z0-9]+)', '([A-Za-z.]*)'", table)
+    want = [("object", ""), ("object", "log"), ("optionalString", "adminIp"), ("optionalObject", "aliases"),
+            ("string", "domain"), ("object", "registration"), ("string", "registration.type"),
+            ("optionalNumber", "registration.ttl"), ("optionalArrayOfNumber", "registration.ports"),
+            ("optionalObject", "registration.service"), ("string", "registration.service.type"),
+            ("isServiceType", "registration.service.type"), ("object", "registration.service.service"),
+            ("string", "registration.service.service.srvce"), ("string", "registration.service.service.proto"),
+            ("optionalNumber", "registration.service.service.ttl"), ("defaultTtl60", "registration.service.service"),
+            ("number", "registration.service.service.port"), ("object", "zk")]
+    assert rows == want

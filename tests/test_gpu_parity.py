@@ -164,7 +164,7 @@ def test_out_of_domain_is_an_error_not_a_fallback(ctx):
 
 def test_rejected_type_names(ctx):
     from registrar_b200._native import OutOfDomainError
-    for t in ("type", "address", "ttl", "0", "42"):
+    for t in ("type", "address", "ttl", "0", "42", "__proto__"):
         with pytest.raises(OutOfDomainError):
             ctx.set_types([t])
     ctx.set_types(["00", "quote\"d", "host"])     # "00" is not an array index; escapes are applied on the host
@@ -233,6 +233,31 @@ def test_corrupt_offsets_are_refused_not_dereferenced(ctx):
         assert ei.value.result.bad_bits & BAD_TOO_LARGE
         setattr(batch, field, saved)
     assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
+
+
+def test_corrupt_offsets_on_the_pipelined_host_path(ctx):
+    """with n >= 2 * chunk_records the host path copies [off[r0], off[r1]) per chunk; a corrupt offset AT
+    a chunk boundary must be reported (REGK_BAD_TOO_LARGE), not used as a memcpy range."""
+    from registrar_b200._native import OutOfDomainError
+    from registrar_b200.batch import BAD_TOO_LARGE
+    batch = synth.generate("config3", n=6000)
+    ctx.set_option("chunk_records", 1024)
+    try:
+        want = oracle.register_batch(batch)
+        assert_same(ctx.register_batch(batch), want)              # the pipelined path itself (6 chunks)
+        for field, idx, val in [("domain_off", 2048, 2 ** 31), ("domain_off", 1024, 3), ("addr_off", 3072, 2 ** 30),
+                                ("ports_off", 4096, 2 ** 29), ("domain_off", 2049, 2 ** 31), ("addr_off", 5000, 1)]:
+            arr = getattr(batch, field).copy()
+            saved = getattr(batch, field)
+            arr[idx] = val
+            setattr(batch, field, arr)
+            with pytest.raises(OutOfDomainError) as ei:
+                ctx.register_batch(batch)
+            assert ei.value.result.bad_bits & BAD_TOO_LARGE, (field, idx)
+            setattr(batch, field, saved)
+        assert_same(ctx.register_batch(batch), want)
+    finally:
+        ctx.set_option("chunk_records", 262144)
 
 
 def test_short_last_tile_at_every_output_phase(ctx):

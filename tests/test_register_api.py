@@ -59,10 +59,13 @@ def test_argument_assertions_throw_synchronously():
 
 
 def test_heartbeat_retry_semantics():
-    # lib/zk.js:21-44: 5 attempts, 1 s doubling to 30 s
+    # lib/zk.js:21-44: backoff `failAfter(5)` = 5 retries after the first call (6 stat rounds), 1 s doubling to 30 s
     from registrar_b200.zk import heartbeat, patch_client
     zk = FakeZk()
     zk.nodes["/a"] = {"data": b"{}", "ephemeral": True}
+    zk.stats = []
+    real_stat = zk.stat
+    zk.stat = lambda path, cb: (zk.stats.append(path), real_stat(path, cb))[1]
     delays, out = [], []
     heartbeat({"nodes": ["/a"], "zk": zk}, lambda err=None: out.append(err), _timer=lambda ms, fn: (delays.append(ms), fn()))
     assert out == [None] and delays == []
@@ -70,11 +73,12 @@ def test_heartbeat_retry_semantics():
     heartbeat({"nodes": ["/a", "/missing"], "zk": zk}, lambda err=None: out.append(err),
               _timer=lambda ms, fn: (delays.append(ms), fn()))
     assert len(out) == 1 and getattr(out[0], "name", None) == "NO_NODE"
-    assert delays == [1000, 2000, 4000, 8000]
+    assert delays == [1000, 2000, 4000, 8000, 16000]
+    assert zk.stats.count("/missing") == 6                  # first call + 5 retries
     delays.clear(); out.clear()
     heartbeat({"nodes": ["/missing"], "zk": zk, "retry": {"maxAttempts": 3, "initialDelay": 20000, "maxDelay": 30000}},
               lambda err=None: out.append(err), _timer=lambda ms, fn: (delays.append(ms), fn()))
-    assert delays == [20000, 30000] and out[0] is not None
+    assert delays == [20000, 30000, 30000] and out[0] is not None
     with pytest.raises(AssertionError):
         heartbeat({"nodes": "x", "zk": zk}, lambda *a: None)
     patch_client(zk)
@@ -192,3 +196,15 @@ def test_domain_to_path_and_register_batch(built):
     res = register_batch([{"domain": "authcache.emy-10.joyent.us", "hostname": "a2674d3b-a9c4-46bc-a835-b6ce21d522c2",
                            "type": "redis_host", "address": "172.27.10.62", "ttl": 30, "ports": [6379]}])
     assert res.path(0) == b"/us/joyent/emy-10/authcache/a2674d3b-a9c4-46bc-a835-b6ce21d522c2"
+
+
+def test_from_records_refuses_numbers_the_kernels_cannot_print():
+    # ttl 1.5 became "ttl":1, ttl -2**31 collided with the "absent" sentinel, ports wrapped
+    from registrar_b200.batch import RecordBatch
+    base = {"domain": "a.b", "hostname": "h", "type": "host", "address": "1.2.3.4"}
+    for bad in ({"ttl": 1.5}, {"ttl": -2 ** 31}, {"ttl": 2 ** 31}, {"ports": [-1]}, {"ports": [2 ** 32]},
+                {"ports": [80.5]}, {"ttl": True}, {"ports": ["80"]}):
+        with pytest.raises(ValueError):
+            RecordBatch.from_records([dict(base, **bad)], types=["host"])
+    ok = RecordBatch.from_records([dict(base, ttl=30.0, ports=[0, 2 ** 32 - 1])], types=["host"])
+    assert int(ok.ttl[0]) == 30 and list(ok.ports) == [0, 2 ** 32 - 1]
