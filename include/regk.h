@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define REGK_ABI_VERSION 2
+#define REGK_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------ */
 #define REGK_OK                 0
@@ -52,6 +52,9 @@ extern "C" {
                                        (lib/register.js:223); default = host nodes (A2, lib/register.js:222) */
 #define REGK_NO_JSON     (1u << 3)  /* paths only (skip A3/A4) */
 #define REGK_NO_PATH     (1u << 4)  /* payloads only (skip A1/A2) */
+#define REGK_JOB_STEP    (1u << 5)  /* this batch is the calling rank's shard of the multi-GPU job bound with
+                                       regk_job_bind(): results go straight into every rank's whole-job buffers
+                                       (requires REGK_IN_DEVICE | REGK_OUT_DEVICE, paths and payloads) */
 
 /* ---- per-record validation bits (regk_result.bad_bits) ------------------ */
 #define REGK_BAD_DOMAIN_BYTE  (1u << 0)  /* byte >= 0x80 or '/' in a domain (JS toLowerCase / path.normalize
@@ -126,6 +129,11 @@ typedef struct regk_result {
     float           json_len_kernel_ms; /* regk_json_len_kernel (payload lengths + tile bases) */
     uint32_t        launches;       /* kernels launched by this call */
     void           *opaque;         /* library bookkeeping */
+    /* REGK_JOB_STEP only: where this rank's shard sits in the job-wide streams and how long those are.  The
+       result pointers above are then the rank's own WHOLE-JOB buffers (offsets job-absolute, n_total + 1
+       entries); path_total / json_total stay the shard's own byte counts. */
+    uint64_t        job_path_base, job_path_total;
+    uint64_t        job_json_base, job_json_total;
 } regk_result;
 
 /* ---- lifecycle ----------------------------------------------------------- */
@@ -202,6 +210,42 @@ typedef struct regk_gather {
  * barrier across ranks (e.g. a 1-element NCCL all-reduce).  Out-of-range totals raise REGK_ERR_INVALID_ARG
  * at regk_sync time through the returned device flag, never a wild store. */
 int         regk_gather_push(regk_ctx *ctx, const regk_result *shard, const regk_gather *g);
+
+/*
+ * ---- the multi-GPU job with the all-gather FUSED into the compose kernels ---------------------------------------
+ * BASELINE.json configs[3]/[4]: "the record batch shards across the GPUs of one box, one all-gather reassembles
+ * the output byte stream".  Here the reassembly is not a separate pass: every rank's regk_path_kernel /
+ * regk_json_kernel place each tile at its FINAL position of the job-wide stream and store it, straight out of
+ * shared memory (TMA bulk copies, byte-masked at the tile's ragged ends), into the whole-job buffers of ALL ranks
+ * over NVLink / NVSwitch, offsets included.  What the ranks must know of each other is two numbers per shard - its
+ * path bytes (closed form in the input sizes) and its payload bytes (known after the path kernel's side job) - and
+ * those travel through a peer-memory mailbox (regk_peersync.cuh): a 16-byte all-gather + barrier written as a
+ * one-warp kernel, no library collective on the data path.  One step on every rank:
+ *     exchange(path totals)  ->  regk_path_kernel (push)  ->  exchange(payload totals)  ->  regk_json_kernel (push)
+ *     ->  exchange (closing barrier: every rank's stores have landed everywhere)
+ * all enqueued on the context's stream by ONE regk_register_batch(REGK_JOB_STEP) call.  The first exchange doubles
+ * as the entry barrier: a rank starts overwriting its peers' buffers only after every rank's stream has reached
+ * this step, i.e. has finished whatever it had enqueued on the previous step's results.
+ * A shard with empty labels (path.join drops them, so the closed-form placement fails) is refused with
+ * REGK_ERR_STATE at regk_finish: run it unfused (plain batch + regk_gather_push).
+ */
+#define REGK_MAILBOX_BYTES (REGK_MAX_PEERS * 32)    /* one 32-byte slot per sender; zero it once after allocation */
+
+typedef struct regk_job {
+    uint32_t world, rank;
+    uint64_t rec_base;              /* records held by the ranks before this one */
+    uint64_t n_total;               /* records of the whole job */
+    void *path_bytes[REGK_MAX_PEERS];       /* rank q's whole-job buffers as mapped in THIS process ([rank] = own) */
+    uint64_t *path_off[REGK_MAX_PEERS];     /* uint64 [n_total + 1] */
+    void *json_bytes[REGK_MAX_PEERS];
+    uint64_t *json_off[REGK_MAX_PEERS];
+    uint64_t *mailbox[REGK_MAX_PEERS];      /* REGK_MAILBOX_BYTES each, zeroed once */
+    uint64_t path_cap, json_cap;    /* bytes behind every whole-job byte buffer */
+    uint64_t timeout_ms;            /* how long an exchange waits for a silent peer before failing (0 = 10 s) */
+} regk_job;
+
+/* Bind (copy) the job description to the context; NULL unbinds.  No batch may be pending. */
+int         regk_job_bind(regk_ctx *ctx, const regk_job *job);
 
 /*
  * ---- setupDirectories for a batch (reference lib/register.js:107-125: mkdirp(path.dirname(n)) for every node) ----

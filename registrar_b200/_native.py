@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-from .batch import (FLAG_IN_DEVICE, FLAG_NODE_ALIAS, FLAG_NO_JSON, FLAG_NO_PATH, FLAG_OUT_DEVICE,
+from .batch import (FLAG_IN_DEVICE, FLAG_JOB_STEP, FLAG_NODE_ALIAS, FLAG_NO_JSON, FLAG_NO_PATH, FLAG_OUT_DEVICE,
                     RecordBatch)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -57,7 +57,9 @@ class CResult(C.Structure):          # regk_result
                 ("path_bytes", C.c_void_p), ("path_off", C.c_void_p), ("path_total", C.c_uint64),
                 ("json_bytes", C.c_void_p), ("json_off", C.c_void_p), ("json_total", C.c_uint64),
                 ("kernel_ms", C.c_float), ("path_kernel_ms", C.c_float), ("json_kernel_ms", C.c_float),
-                ("json_len_kernel_ms", C.c_float), ("launches", C.c_uint32), ("opaque", C.c_void_p)]
+                ("json_len_kernel_ms", C.c_float), ("launches", C.c_uint32), ("opaque", C.c_void_p),
+                ("job_path_base", C.c_uint64), ("job_path_total", C.c_uint64),
+                ("job_json_base", C.c_uint64), ("job_json_total", C.c_uint64)]
 
 
 MAX_PEERS = 16
@@ -72,6 +74,17 @@ class CGather(C.Structure):          # regk_gather
                 ("path_cap", C.c_uint64), ("json_cap", C.c_uint64)]
 
 
+MAILBOX_BYTES = MAX_PEERS * 32
+
+
+class CJob(C.Structure):             # regk_job
+    _fields_ = [("world", C.c_uint32), ("rank", C.c_uint32), ("rec_base", C.c_uint64), ("n_total", C.c_uint64),
+                ("path_bytes", C.c_void_p * MAX_PEERS), ("path_off", C.c_void_p * MAX_PEERS),
+                ("json_bytes", C.c_void_p * MAX_PEERS), ("json_off", C.c_void_p * MAX_PEERS),
+                ("mailbox", C.c_void_p * MAX_PEERS),
+                ("path_cap", C.c_uint64), ("json_cap", C.c_uint64), ("timeout_ms", C.c_uint64)]
+
+
 class CParents(C.Structure):         # regk_parents
     _fields_ = [("n", C.c_uint64), ("n_unique", C.c_uint64), ("flags", C.c_uint32), ("launches", C.c_uint32),
                 ("parent_len", C.c_void_p), ("unique_first", C.c_void_p), ("kernel_ms", C.c_float)]
@@ -81,7 +94,7 @@ EXPORTS = ["regk_abi_version", "regk_create", "regk_destroy", "regk_last_error",
            "regk_set_types", "regk_register_batch", "regk_finish", "regk_release", "regk_host_alloc",
            "regk_host_free", "regk_dev_alloc", "regk_dev_free", "regk_memcpy_h2d", "regk_memcpy_d2h",
            "regk_sync", "regk_set_option", "regk_get_option", "regk_ipc_export", "regk_ipc_open", "regk_ipc_close",
-           "regk_gather_push", "regk_parent_dirs"]
+           "regk_gather_push", "regk_parent_dirs", "regk_job_bind"]
 
 _lib = None
 
@@ -127,6 +140,7 @@ def load_library():
     lib.regk_ipc_close.argtypes = [vp, vp]
     lib.regk_gather_push.argtypes = [vp, C.POINTER(CResult), C.POINTER(CGather)]
     lib.regk_parent_dirs.argtypes = [vp, u32, C.POINTER(CParents)]
+    lib.regk_job_bind.argtypes = [vp, C.POINTER(CJob)]
     _lib = lib
     return lib
 
@@ -355,6 +369,15 @@ class Context:
 
     def gather_push(self, shard: CResult, plan: CGather):
         self._check(self._lib.regk_gather_push(self._h, C.byref(shard), C.byref(plan)))
+
+    def job_bind(self, job: Optional[CJob]):
+        """Bind the multi-GPU job description (regk_job) to the context; None unbinds."""
+        self._check(self._lib.regk_job_bind(self._h, C.byref(job) if job is not None else None))
+
+    def memset_dev(self, dev_ptr: int, nbytes: int):
+        """Zero device memory allocated with dev_alloc (stream-synchronous helper for non-CUDA hosts)."""
+        z = np.zeros(nbytes, np.uint8)
+        self._check(self._lib.regk_memcpy_h2d(self._h, C.c_void_p(dev_ptr), z.ctypes.data_as(C.c_void_p), nbytes))
 
     def host_alloc(self, nbytes: int) -> int:
         p = self._lib.regk_host_alloc(self._h, nbytes)

@@ -23,6 +23,7 @@ FLAG_OUT_DEVICE = 1 << 1
 FLAG_NODE_ALIAS = 1 << 2
 FLAG_NO_JSON = 1 << 3
 FLAG_NO_PATH = 1 << 4
+FLAG_JOB_STEP = 1 << 5
 
 BAD_DOMAIN_BYTE = 1 << 0
 BAD_HOST_BYTE = 1 << 1

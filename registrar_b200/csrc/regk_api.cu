@@ -21,6 +21,7 @@
 #include "../../include/regk.h"
 #include "regk_kernels.cuh"
 #include "regk_gather.cuh"
+#include "regk_peersync.cuh"
 #include "regk_parents.cuh"
 #include "regk_types.hpp"
 
@@ -73,7 +74,15 @@ struct regk_ctx {
     };
     HostSet hset[2];
     uint64_t hseq = 0;
-    uint32_t *h_gather_flag = nullptr;          /* pinned: regk_gather_push found the whole-job buffers too small */
+    uint32_t *h_gather_flag = nullptr;          /* pinned: 1 = regk_gather_push found the whole-job buffers too small,
+                                                   2 = a peer exchange of a job step timed out */
+    /* multi-GPU job (regk_job_bind): description, exchange sequence number, per-slot bases {path base, path all,
+       rec base, n all, payload base, payload all, -, -} on the device and their pinned host copies */
+    regk_job job{};
+    bool job_bound = false;
+    unsigned long long job_seq = 0;
+    DevBuf job_bases;
+    unsigned long long *h_job_bases = nullptr;
     /* device copy of the path stream of the batch finished last (regk_parent_dirs works on it) */
     const uint8_t *last_path_bytes = nullptr;
     const unsigned long long *last_path_off = nullptr;
@@ -100,7 +109,7 @@ struct regk_ctx {
        "async" option several batches may be enqueued back to back (benchmark loops), each one
        overwriting the previous batch's outputs in stream order. */
     struct Slot {
-        cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     /* [5]: after a job step's closing exchange */
         PathParams path_params{};               /* kept for the exact-offset redo (empty labels) */
         size_t path_smem = 0;
         bool path_alias = false, did_path = false;
@@ -115,6 +124,7 @@ struct regk_ctx {
         const uint32_t *dev_host_off = nullptr;         /* how its paths end: hostname lengths (NULL: fixed stride) */
         uint32_t host_stride = 0;
         bool alias = false;
+        bool job = false;                       /* a REGK_JOB_STEP batch */
         bool in_use = false;
         uint64_t n = 0;
         uint32_t flags = 0;
@@ -601,6 +611,10 @@ void regk_destroy(regk_ctx *ctx)
         cudaFreeHost(ctx->h_status_block);
     if (ctx->h_gather_flag)
         cudaFreeHost(ctx->h_gather_flag);
+    if (ctx->h_job_bases)
+        cudaFreeHost(ctx->h_job_bases);
+    if (ctx->job_bases.p)
+        cudaFree(ctx->job_bases.p);
     for (DevBuf *b : {&ctx->par_len, &ctx->par_slot, &ctx->par_table, &ctx->par_totals, &ctx->par_unique})
         if (b->p)
             cudaFree(b->p);
@@ -833,6 +847,77 @@ int regk_gather_push(regk_ctx *ctx, const regk_result *shard, const regk_gather 
     return REGK_OK;
 }
 
+int regk_job_bind(regk_ctx *ctx, const regk_job *job)
+{
+    if (!ctx)
+        return REGK_ERR_INVALID_ARG;
+    if (ctx->pending)
+        return fail(ctx, REGK_ERR_STATE, "regk_job_bind: a batch is still pending; call regk_finish first");
+    if (!job) {
+        ctx->job_bound = false;
+        return REGK_OK;
+    }
+    if (job->world == 0 || job->world > REGK_MAX_PEERS || job->rank >= job->world)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_job_bind: world %u / rank %u out of range (at most %d ranks)", job->world,
+            job->rank, REGK_MAX_PEERS);
+    for (uint32_t q = 0; q < job->world; q++)
+        if (!job->path_bytes[q] || !job->path_off[q] || !job->json_bytes[q] || !job->json_off[q] || !job->mailbox[q] ||
+            (((uintptr_t)job->path_bytes[q] | (uintptr_t)job->json_bytes[q]) & 15) ||
+            (((uintptr_t)job->path_off[q] | (uintptr_t)job->json_off[q] | (uintptr_t)job->mailbox[q]) & 7))
+            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_job_bind: buffer of rank %u missing or misaligned", q);
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_dev(ctx, ctx->job_bases, (size_t)regk_ctx::NSLOTS * 64);
+    if (rc)
+        return rc;
+    if (!ctx->h_job_bases)
+        CK(cudaMallocHost((void **)&ctx->h_job_bases, (size_t)regk_ctx::NSLOTS * 64));
+    if (!ctx->h_gather_flag) {
+        CK(cudaMallocHost((void **)&ctx->h_gather_flag, sizeof(uint32_t)));
+        *ctx->h_gather_flag = 0;
+    }
+    ctx->job = *job;
+    ctx->job_bound = true;
+    return REGK_OK;
+}
+
+/* one exchange of a job step on the context's stream (regk_peersync.cuh) */
+static int launch_exchange(regk_ctx *ctx, unsigned long long v0, unsigned long long v1, const unsigned long long *src0,
+    uint32_t n0, unsigned long long *bases, unsigned long long *close0)
+{
+    const regk_job &j = ctx->job;
+    ExchangeParams e{};
+    e.world = j.world;
+    e.rank = j.rank;
+    e.seq = ++ctx->job_seq;
+    for (uint32_t q = 0; q < j.world; q++)
+        e.mailbox[q] = (unsigned long long *)j.mailbox[q];
+    e.v0 = v0;
+    e.v1 = v1;
+    e.src0 = src0;
+    e.n0 = n0;
+    e.bases = bases;
+    e.close0 = close0;
+    e.close1 = nullptr;
+    e.host_flag = ctx->h_gather_flag;
+    e.timeout_ns = (j.timeout_ms ? j.timeout_ms : 10000ull) * 1000000ull;
+    regk_peer_exchange_kernel<<<1, 32, 0, ctx->stream>>>(e);
+    CK(cudaGetLastError());
+    return REGK_OK;
+}
+
+static void fill_peers(PeerDst &pd, const regk_job &j, void *const *bytes, uint64_t *const *off)
+{
+    pd.n = 0;
+    pd.job = 1;
+    for (uint32_t q = 0; q < j.world; q++) {
+        if (q == j.rank)
+            continue;
+        pd.bytes[pd.n] = (uint8_t *)bytes[q];
+        pd.off[pd.n] = (unsigned long long *)off[q] + j.rec_base;
+        pd.n++;
+    }
+}
+
 int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
 {
     if (!ctx || !b || !res)
@@ -850,8 +935,18 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     const bool alias = b->flags & REGK_NODE_ALIAS;
     const bool do_path = !(b->flags & REGK_NO_PATH);
     const bool do_json = !(b->flags & REGK_NO_JSON);
+    const bool job = b->flags & REGK_JOB_STEP;
     if (n >= (1ull << 32))
         return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: n must be < 2^32 per call");
+    if (job) {
+        if (!ctx->job_bound)
+            return fail(ctx, REGK_ERR_STATE, "regk_register_batch: REGK_JOB_STEP without a bound job (regk_job_bind)");
+        if (!in_dev || !out_dev || !do_path || !do_json)
+            return fail(ctx, REGK_ERR_INVALID_ARG,
+                "regk_register_batch: a job step is device-resident (REGK_IN_DEVICE | REGK_OUT_DEVICE) and produces paths and payloads");
+        if (ctx->job.rec_base + n > ctx->job.n_total)
+            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_register_batch: the shard's record range lies outside the job");
+        }
     if (do_json && ctx->types.empty())
         return fail(ctx, REGK_ERR_STATE, "regk_register_batch: call regk_set_types first");
     if (n && do_path && (!b->domain_off || (!b->domain_bytes && b->domain_bytes_len)))
@@ -951,9 +1046,17 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     const uint64_t json_cap = do_json ? n * (uint64_t)(38 + 2 * ctx->max_type_q + 4 + 18 + 11) + 2 * addr_len +
         11 * ports_len + 16 : 16;
     int rc;
-    if ((rc = ensure_dev(ctx, o_path_bytes, path_cap)) || (rc = ensure_dev(ctx, o_path_off, (n + 1) * 8)) ||
-        (rc = ensure_dev(ctx, o_json_bytes, json_cap)) || (rc = ensure_dev(ctx, o_json_off, (n + 1) * 8)))
+    if (!job && ((rc = ensure_dev(ctx, o_path_bytes, path_cap)) || (rc = ensure_dev(ctx, o_path_off, (n + 1) * 8)) ||
+        (rc = ensure_dev(ctx, o_json_bytes, json_cap)) || (rc = ensure_dev(ctx, o_json_off, (n + 1) * 8))))
         return rc;
+    /* job step: the outputs are the rank's own whole-job buffers, every position job-absolute */
+    const regk_job &J = ctx->job;
+    uint8_t *const out_path_bytes = job ? (uint8_t *)J.path_bytes[J.rank] : (uint8_t *)o_path_bytes.p;
+    unsigned long long *const out_path_off = job ? (unsigned long long *)J.path_off[J.rank] + J.rec_base : (unsigned long long *)o_path_off.p;
+    uint8_t *const out_json_bytes = job ? (uint8_t *)J.json_bytes[J.rank] : (uint8_t *)o_json_bytes.p;
+    unsigned long long *const out_json_off = job ? (unsigned long long *)J.json_off[J.rank] + J.rec_base : (unsigned long long *)o_json_off.p;
+    const uint64_t out_path_cap = job ? J.path_cap : path_cap, out_json_cap = job ? J.json_cap : json_cap;
+    unsigned long long *const d_bases = job ? (unsigned long long *)ctx->job_bases.p + 8 * (ctx->seq % regk_ctx::NSLOTS) : nullptr;
 
     /* ---- workspace: status | running payload totals per chunk | two-level byte totals of both halves ---- */
     const uint64_t ntiles = (n + TILE - 1) / TILE;
@@ -1000,7 +1103,7 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     }
     DevStatus *d_status = (DevStatus *)wk;
 
-    if (n == 0) {
+    if (n == 0 && !job) {
         CK(cudaMemsetAsync(o_path_off.p, 0, 8, s));
         CK(cudaMemsetAsync(o_json_off.p, 0, 8, s));
     }
@@ -1016,9 +1119,13 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         pp.host_bytes = (const uint8_t *)dev[2];
         pp.host_off = (const uint32_t *)dev[3];
         pp.host_stride = b->host_stride;
-        pp.out_bytes = (uint8_t *)o_path_bytes.p;
-        pp.out_off = (unsigned long long *)o_path_off.p;
-        pp.out_capacity = path_cap;
+        pp.out_bytes = out_path_bytes;
+        pp.out_off = out_path_off;
+        pp.out_capacity = out_path_cap;
+        if (job) {
+            pp.bias_in = d_bases;
+            fill_peers(pp.peer, J, J.path_bytes, J.path_off);
+        }
         pp.exact = 0;                           /* closed-form offsets; see regk_finish for the exact redo */
         pp.tile_total = (uint32_t *)(wk + totals_p_off);
         pp.super_total = (unsigned long long *)(wk + super_p_off);
@@ -1069,9 +1176,13 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         jp.frag_blob = (const uint8_t *)ctx->blob_dev.p;
         jp.ntypes = (uint32_t)ctx->types.size();
         jp.blob_bytes = (uint32_t)ctx->blob_host.size();
-        jp.out_bytes = (uint8_t *)o_json_bytes.p;
-        jp.out_off = (unsigned long long *)o_json_off.p;
-        jp.out_capacity = json_cap;
+        jp.out_bytes = out_json_bytes;
+        jp.out_off = out_json_off;
+        jp.out_capacity = out_json_cap;
+        if (job) {
+            jp.base_in = d_bases + 4;
+            fill_peers(jp.peer, J, J.json_bytes, J.json_off);
+        }
         jp.tile_total = (uint32_t *)(wk + totals_j_off);
         jp.super_total = (unsigned long long *)(wk + super_j_off);
         jp.status = d_status;
@@ -1128,8 +1239,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     uint32_t launches = 0;
     slot.did_path = false;
     slot.d_status = d_status;
-    slot.dev_path_bytes = (n && do_path) ? pp.out_bytes : nullptr;
-    slot.dev_path_off = (n && do_path) ? pp.out_off : nullptr;
+    slot.dev_path_bytes = (n && do_path && !job) ? pp.out_bytes : nullptr;    /* regk_parent_dirs: not on job steps */
+    slot.dev_path_off = (n && do_path && !job) ? pp.out_off : nullptr;
     slot.dev_host_off = pp.host_off;
     slot.host_stride = pp.host_stride;
     slot.alias = alias;
@@ -1139,6 +1250,14 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     const int64_t time_every = std::max<int64_t>(1, opt_get(ctx, "time_every", 1));
     const bool timed = ctx->seq % (uint64_t)time_every == 0;
     slot.timed = timed;
+    if (job) {
+        /* exchange 1 (entry barrier): closed-form path bytes of every shard -> this rank's path base; the job's
+           closing path offset lands in this rank's own offset array */
+        const uint64_t my_paths = dom_len + host_len + (alias ? 1 : 2) * n;
+        if ((rc = launch_exchange(ctx, my_paths, n, nullptr, 0, d_bases, (unsigned long long *)J.path_off[J.rank] + J.n_total)))
+            return rc;
+        launches++;
+    }
     if (timed)
         CK(cudaEventRecord(slot.ev[0], s));
     if (n && do_path) {
@@ -1155,6 +1274,14 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     }
     if (timed)
         CK(cudaEventRecord(slot.ev[1], s));
+    if (job) {
+        /* exchange 2: payload bytes of every shard (sum of the super-tile totals the path kernel's side job left)
+           -> this rank's payload base */
+        if ((rc = launch_exchange(ctx, 0, 0, n ? jp.super_total : nullptr, n ? (uint32_t)nsuper_chunk : 0, d_bases + 4,
+                 (unsigned long long *)J.json_off[J.rank] + J.n_total)))
+            return rc;
+        launches++;
+    }
     if (n && do_json) {
         if (!fused_len) {
             const unsigned len_grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 8);
@@ -1171,10 +1298,19 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         CK(cudaEventRecord(slot.ev[2], s));
     }
     CK(cudaEventRecord(slot.ev[3], s));
+    if (job) {
+        /* exchange 3 (closing barrier): once it has passed, every rank's tiles and offsets are in this rank's buffers */
+        if ((rc = launch_exchange(ctx, 0, 0, nullptr, 0, nullptr, nullptr)))
+            return rc;
+        launches++;
+        CK(cudaEventRecord(slot.ev[5], s));
+    }
     if (ring >= 0) {
         /* off the main stream: status read-back, then re-zero this workspace for its next turn */
-        CK(cudaStreamWaitEvent(ctx->s_side, slot.ev[3], 0));
+        CK(cudaStreamWaitEvent(ctx->s_side, job ? slot.ev[5] : slot.ev[3], 0));
         CK(cudaMemcpyAsync(slot.h_status, d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, ctx->s_side));
+        if (job)
+            CK(cudaMemcpyAsync(ctx->h_job_bases + 8 * (ctx->seq % regk_ctx::NSLOTS), d_bases, 64, cudaMemcpyDeviceToHost, ctx->s_side));
         CK(cudaEventRecord(slot.ev[4], ctx->s_side));
         CK(cudaMemsetAsync(wk, 0, work_bytes, ctx->s_side));
         CK(cudaEventRecord(ctx->ws_clean[ring], ctx->s_side));
@@ -1187,6 +1323,7 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     }
 
     slot.hset = hs ? (int)(hs - ctx->hset) : -1;
+    slot.job = job;
     slot.d2h_issued = false;
     slot.in_use = true;
     slot.n = n;
@@ -1231,7 +1368,17 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     if (e != cudaSuccess)
         return fail(ctx, REGK_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
     uint32_t extra_launches = 0;
-    if (slot->h_status->needs_exact && !slot->h_status->bad_bits && slot->did_path) {
+    if (slot->job) {
+        if (ctx->h_gather_flag && *ctx->h_gather_flag == 2u) {
+            *ctx->h_gather_flag = 0;
+            return fail(ctx, REGK_ERR_CUDA, "job step: a peer did not reach the exchange in time (mailbox wait timed out)");
+        }
+        if (slot->h_status->needs_exact && !slot->h_status->bad_bits)
+            return fail(ctx, REGK_ERR_STATE,
+                "job step: a domain has empty labels, so the closed-form placement of the fused all-gather does not hold; "
+                "run this shard as a plain batch and reassemble with regk_gather_push");
+    }
+    if (!slot->job && slot->h_status->needs_exact && !slot->h_status->bad_bits && slot->did_path) {
         /* Some domain has empty labels (path.join drops them): the closed-form offsets do not hold.
            Re-run the path half with exact lengths: length kernel + last-CTA scan, then compose. */
         if (ctx->pending && slot->hset < 0)         /* device outputs are single-buffered; host sets are not */
@@ -1297,6 +1444,19 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
         return fail(ctx, REGK_ERR_OUT_OF_DOMAIN,
             "record %llu is outside the supported input domain (REGK_BAD bits 0x%x); no output produced",
             (unsigned long long)res->first_bad, st.bad_bits);
+    }
+    if (slot->job) {
+        const unsigned long long *hb = ctx->h_job_bases + 8 * ((size_t)(slot - ctx->slots));
+        res->flags = REGK_OUT_DEVICE;
+        res->path_bytes = (uint8_t *)ctx->job.path_bytes[ctx->job.rank];
+        res->path_off = ctx->job.path_off[ctx->job.rank];
+        res->json_bytes = (uint8_t *)ctx->job.json_bytes[ctx->job.rank];
+        res->json_off = ctx->job.json_off[ctx->job.rank];
+        res->job_path_base = hb[0];
+        res->job_path_total = hb[1];
+        res->job_json_base = hb[4];
+        res->job_json_total = hb[5];
+        return REGK_OK;
     }
     if (out_dev) {
         res->flags = REGK_OUT_DEVICE;

@@ -37,6 +37,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/regk.h"
 #include "regk_core.cuh"
 
 namespace regk {
@@ -174,6 +175,113 @@ __device__ __forceinline__ void flush_out(uint8_t *gout, const uint8_t *smem, ui
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+/*
+ * ---- multi-GPU job: extra destinations of a tile (include/regk.h regk_job) ----
+ * A rank's compose kernels place their output directly at its final position in the WHOLE-JOB stream
+ * (out_bytes = the rank's own whole-job buffer, offsets biased by the bytes of the ranks before it) and, when
+ * `PeerDst::n` > 0, store every tile a second, third ... time into the same position of the peers' whole-job
+ * buffers (CUDA-IPC mapped, so a store travels over NVLink / NVSwitch): the all-gather is fused into the
+ * compose kernels tile by tile, straight out of shared memory, and no rank ever re-reads its shard from HBM.
+ */
+struct PeerDst {
+    uint32_t n;                                     /* number of extra destinations (0: single-GPU behaviour) */
+    uint32_t job;                                   /* 1: output positions are job-absolute (see kernels) */
+    uint8_t *bytes[REGK_MAX_PEERS - 1];             /* the peers' whole-job byte buffers (16-byte aligned) */
+    unsigned long long *off[REGK_MAX_PEERS - 1];    /* the peers' offset arrays, already advanced to this rank's first record */
+};
+
+/* parameter arrays cannot be indexed dynamically without a local-memory copy of the whole block: lanes pick
+   their entry with compile-time indices and park it in shared memory */
+__device__ __forceinline__ void peer_tables(const PeerDst &pd, uint8_t **s_pb, unsigned long long **s_po)
+{
+    const uint32_t t = threadIdx.x;
+    if (t < REGK_MAX_PEERS - 1) {
+        uint8_t *b = nullptr;
+        unsigned long long *o = nullptr;
+        #pragma unroll
+        for (int q = 0; q < REGK_MAX_PEERS - 1; q++)
+            if (t == (uint32_t)q) {
+                b = pd.bytes[q];
+                o = pd.off[q];
+            }
+        s_pb[t] = b;
+        s_po[t] = o;
+    }
+}
+
+/* one 16-byte block of the image with a byte mask: bit i of `mask` = byte i is stored (SASS UBLKCP ... BYTE_MASK) */
+__device__ __forceinline__ void bulk_s2g_masked(uint8_t *gdst, const uint8_t *smem_src, uint32_t mask)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.cp_mask [%0], [%1], 16, %2;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "h"((unsigned short)mask) : "memory");
+}
+
+__device__ __forceinline__ void bulk_s2g(uint8_t *gdst, const uint8_t *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+/*
+ * flush_out for a job tile: the image goes to the rank's own buffer AND to every peer, all by the TMA engine and
+ * all issued by one thread: per destination one bulk copy of the aligned body plus one byte-masked 16-byte copy
+ * for the head and one for the tail (the neighbouring tiles, possibly of another rank, own the other bytes of
+ * those blocks) - no byte-sized stores on NVLink.  Same preconditions as flush_out.
+ */
+__device__ __forceinline__ void flush_out_job(uint8_t *gout, uint8_t *const *s_pb, uint32_t npeers, const uint8_t *smem,
+    uint64_t gbase, uint32_t total)
+{
+    if (threadIdx.x != 0 || total == 0)
+        return;
+    const uint64_t a0 = gbase & ~15ull;
+    const uint32_t lo = (uint32_t)(gbase - a0);
+    const uint32_t hi = lo + total;
+    const uint32_t b_first = lo >> 4, b_last = (hi - 1u) >> 4;          /* 16-byte blocks of the image that hold bytes */
+    for (uint32_t d = 0; d <= npeers; d++) {
+        uint8_t *g = (d == 0 ? gout : s_pb[d - 1]) + a0;
+        if (b_first == b_last) {
+            const uint32_t m = (0xFFFFu << (lo & 15u)) & (0xFFFFu >> (15u - ((hi - 1u) & 15u)));
+            bulk_s2g_masked(g + 16u * b_first, smem + 16u * b_first, m);
+        } else {
+            uint32_t body_lo = lo, body_hi = hi;
+            if (lo & 15u) {
+                bulk_s2g_masked(g + 16u * b_first, smem + 16u * b_first, 0xFFFFu << (lo & 15u));
+                body_lo = 16u * (b_first + 1u);
+            }
+            if (hi & 15u) {
+                bulk_s2g_masked(g + 16u * b_last, smem + 16u * b_last, 0xFFFFu >> (16u - (hi & 15u)));
+                body_hi = 16u * b_last;
+            }
+            if (body_hi > body_lo)
+                bulk_s2g(g + body_lo, smem + body_lo, body_hi - body_lo);
+        }
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       /* the image must outlive the engine's reads */
+}
+
+/* generic (global-memory) tiles of a job: the CTA has just composed bytes [gbase, gbase + total) into its own
+   buffer; after a barrier it copies that range to the peers (16-byte blocks where whole, bytes at the ends) */
+__device__ __forceinline__ void copy_range_to_peers(const uint8_t *gown, uint8_t *const *s_pb, uint32_t npeers, uint64_t gbase,
+    uint32_t total)
+{
+    const uint64_t end = gbase + total;
+    uint64_t body_lo = (gbase + 15ull) & ~15ull, body_hi = end & ~15ull;
+    if (body_hi <= body_lo)
+        body_lo = body_hi = end;
+    for (uint64_t b = body_lo + 16ull * threadIdx.x; b < body_hi; b += 16ull * TILE) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(gown + b);
+        for (uint32_t q = 0; q < npeers; q++)
+            stg_v4(s_pb[q] + b, v);
+    }
+    for (uint64_t i = gbase + threadIdx.x; i < body_lo; i += TILE)
+        for (uint32_t q = 0; q < npeers; q++)
+            s_pb[q][i] = gown[i];
+    for (uint64_t i = body_hi + threadIdx.x; i < end; i += TILE)
+        for (uint32_t q = 0; q < npeers; q++)
+            s_pb[q][i] = gown[i];
+}
+
 /* Block-wide exclusive scan of one value per thread (two barriers). */
 template <typename T>
 __device__ __forceinline__ T block_scan(T *warp_sum /* smem[WARPS] */, T v, T *total)
@@ -272,6 +380,7 @@ struct JsonParams {
     uint64_t addr_limit, ports_limit;   /* bytes behind addr_bytes / elements behind ports (trusted) */
     uint32_t out_cap;                   /* shared-memory budget of the output image */
     uint32_t force_generic;
+    PeerDst peer;                       /* multi-GPU job: the other ranks' whole-job payload buffers */
 };
 
 /* everything the payload of record r depends on except the address bytes */
@@ -357,6 +466,8 @@ struct PathParams {
     uint64_t dom_limit, host_limit;     /* bytes behind domain_bytes / host_bytes (trusted, from the caller) */
     uint32_t dom_cap, host_cap, out_cap;        /* shared-memory budgets in bytes */
     uint32_t force_generic;
+    const unsigned long long *bias_in;  /* optional, device: added to off_bias (job: path bytes of the ranks before this one) */
+    PeerDst peer;                       /* multi-GPU job: the other ranks' whole-job path buffers */
 };
 
 /* closed-form offset of record r's path when no label is empty: path_len = L + 2 + H (alias: L + 1) */
@@ -444,6 +555,11 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
     __shared__ uint32_t warp_sum[WARPS];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ TilePlan s_plan;
+    __shared__ uint8_t *s_pb[REGK_MAX_PEERS - 1];
+    __shared__ unsigned long long *s_po[REGK_MAX_PEERS - 1];
+    const uint32_t npeers = p.peer.n;
+    if (npeers)
+        peer_tables(p.peer, s_pb, s_po);                        /* published by the plan barrier */
     uint8_t *s_dom = smem + 16;                                 /* staged domain bytes (16 bytes of front padding):
                                                                    lower-cased, '.' -> '/' */
     uint8_t *s_bits = s_dom + p.dom_cap + 32;                   /* 1 bit per staged domain byte: was '.' */
@@ -496,7 +612,8 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
                 bulk_g2s(s_host, p.host_bytes + (q.HB0 & ~15ull), q.nh, &s_bar);
         }
         /* closed-form placement: slot = L + 2 + H bytes per record (alias: L + 1) */
-        q.tile_base = (unsigned long long)q.D0 + q.HB0 + (unsigned long long)per_rec * r0 + p.off_bias;
+        q.tile_base = (unsigned long long)q.D0 + q.HB0 + (unsigned long long)per_rec * r0 + p.off_bias +
+            (p.bias_in ? *p.bias_in : 0ull);
         q.tile_total = dom_span + host_span + per_rec * nrec;
         q.host_span = host_span;
         q.flags = (broken ? PLAN_BROKEN : 0u) | (fits ? PLAN_FITS : 0u) | (bulk ? PLAN_BULK : 0u);
@@ -537,7 +654,7 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
     uint32_t tile_total = s_plan.tile_total;
     bool room = flags & PLAN_ROOM;
     if (exact) {
-        tile_base = *reinterpret_cast<const unsigned long long *>(warp_sum) + p.off_bias;
+        tile_base = *reinterpret_cast<const unsigned long long *>(warp_sum) + p.off_bias + (p.bias_in ? *p.bias_in : 0ull);
         tile_total = p.tile_total[tile];
         room = !(flags & PLAN_BROKEN) && tile_base + tile_total <= p.out_capacity;
         __syncthreads();                                        /* warp_sum is about to be reused by block_scan */
@@ -605,8 +722,11 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         } else if (live && len != slot) {
             atomicOr(&p.status->needs_exact, 1u);               /* empty labels: redo with exact offsets */
         }
-        if (live)
+        if (live) {
             p.out_off[r] = tile_base + local;
+            for (uint32_t q = 0; q < npeers; q++)
+                s_po[q][r] = tile_base + local;
+        }
         if (room) {
             WordSink sink;
             sink.init(reinterpret_cast<uint32_t *>(s_out), local + ((uint32_t)tile_base & 15u));
@@ -621,7 +741,10 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
                 sink.tail();                                    /* phase B: shared boundary words */
             fence_proxy_async();
             __syncthreads();
-            flush_out(p.out_bytes, s_out, tile_base, tile_total);
+            if (npeers)
+                flush_out_job(p.out_bytes, s_pb, npeers, s_out, tile_base, tile_total);
+            else
+                flush_out(p.out_bytes, s_out, tile_base, tile_total);
         }
     } else {
         /* generic path: compose straight from / to global memory */
@@ -640,12 +763,19 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         } else if (live && len != slot) {
             atomicOr(&p.status->needs_exact, 1u);
         }
-        if (live)
+        if (live) {
             p.out_off[r] = tile_base + local;
+            for (uint32_t q = 0; q < npeers; q++)
+                s_po[q][r] = tile_base + local;
+        }
         if (room && live && rec_ok) {
             ByteSink sink;
             sink.init(p.out_bytes + tile_base + local);
             emit_path<ALIAS>(dsrc, d0, L, hsrc, hoff, H, sink);
+        }
+        if (npeers && room) {                                   /* CTA-uniform */
+            __syncthreads();
+            copy_range_to_peers(p.out_bytes, s_pb, npeers, tile_base, tile_total);
         }
     }
     if (!room && !(flags & PLAN_BROKEN) && t == 0)
@@ -653,8 +783,14 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
     if (live)
         report_bad(p.status, bad, p.rec0 + r);
     if (r0 + nrec == p.n && t == 0) {
-        p.out_off[p.n] = tile_base + tile_total;
-        p.status->path_total = tile_base + tile_total;
+        if (p.peer.job) {
+            /* job: the entry after the shard's last record belongs to the next rank (or is the job's closing
+               entry, written by the exchange kernel); report the shard's own byte count */
+            p.status->path_total = tile_base + tile_total - (p.bias_in ? *p.bias_in : 0ull) - p.off_bias;
+        } else {
+            p.out_off[p.n] = tile_base + tile_total;
+            p.status->path_total = tile_base + tile_total;
+        }
     }
 }
 
@@ -698,6 +834,11 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const J
     __shared__ uint32_t warp_sum[WARPS];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ JsonPlan s_plan;
+    __shared__ uint8_t *s_pb[REGK_MAX_PEERS - 1];
+    __shared__ unsigned long long *s_po[REGK_MAX_PEERS - 1];
+    const uint32_t npeers = p.peer.n;
+    if (npeers)
+        peer_tables(p.peer, s_pb, s_po);                        /* published by the scan's barriers */
     uint8_t *s_blob = smem;
     uint8_t *s_out = smem + p.blob_bytes;
 
@@ -768,8 +909,11 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const J
     const unsigned long long tile_base = s_plan.tile_base;
     const uint32_t tile_total = s_plan.tile_total;
     const uint32_t flags = s_plan.flags;
-    if (live)
+    if (live) {
         p.out_off[r] = tile_base + local;
+        for (uint32_t q = 0; q < npeers; q++)
+            s_po[q][r] = tile_base + local;
+    }
 
     const PaddedWords blob{reinterpret_cast<const uint32_t *>(s_blob)};
     const uint32_t *ports = p.ports + m.p0;
@@ -787,19 +931,32 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const J
             sink.tail();                                        /* phase B: shared boundary words */
         fence_proxy_async();
         __syncthreads();
-        flush_out(p.out_bytes, s_out, tile_base, tile_total);
-    } else if (live) {
-        ByteSink sink;
-        sink.init(p.out_bytes + tile_base + local);
-        emit_json(blob, tf, aw, asrc, a0, al, m.has_ttl, m.ttl, m.has_ports, k, port, sink);
+        if (npeers)
+            flush_out_job(p.out_bytes, s_pb, npeers, s_out, tile_base, tile_total);
+        else
+            flush_out(p.out_bytes, s_out, tile_base, tile_total);
+    } else {
+        if (live) {
+            ByteSink sink;
+            sink.init(p.out_bytes + tile_base + local);
+            emit_json(blob, tf, aw, asrc, a0, al, m.has_ttl, m.ttl, m.has_ports, k, port, sink);
+        }
+        if (npeers) {                                           /* CTA-uniform */
+            __syncthreads();
+            copy_range_to_peers(p.out_bytes, s_pb, npeers, tile_base, tile_total);
+        }
     }
     if (live)
         report_bad(p.status, bad, p.rec0 + r);
     if (r0 + nrec == p.n && t == 0) {
-        p.out_off[p.n] = tile_base + tile_total;
-        p.status->json_total = tile_base + tile_total;
-        if (p.base_out)
-            *p.base_out = tile_base + tile_total;
+        if (p.peer.job) {
+            p.status->json_total = tile_base + tile_total - (p.base_in ? *p.base_in : 0ull);    /* the shard's own bytes */
+        } else {
+            p.out_off[p.n] = tile_base + tile_total;
+            p.status->json_total = tile_base + tile_total;
+            if (p.base_out)
+                *p.base_out = tile_base + tile_total;
+        }
     }
 }
 

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(built):
     for s in syms:
         assert hasattr(lib, s), "libregk.so does not export %s" % s
     assert sorted(_native.EXPORTS) == syms
-    assert lib.regk_abi_version() == 2
+    assert lib.regk_abi_version() == 3
 
 
 def test_no_gpu_means_failure_not_fallback(built):
@@ -49,6 +49,8 @@ def test_struct_layouts_match_header(built):
     #include "regk.h"
     int main(void) {
         printf("%zu %zu %zu ", sizeof(regk_parents), offsetof(regk_parents, unique_first), offsetof(regk_parents, kernel_ms));
+        printf("%zu %zu %zu %zu %zu ", sizeof(regk_job), offsetof(regk_job, mailbox), offsetof(regk_job, timeout_ms),
+               offsetof(regk_result, job_path_base), offsetof(regk_result, job_json_total));
         printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(regk_batch), offsetof(regk_batch, domain_bytes),
                offsetof(regk_batch, ports_present), sizeof(regk_result), offsetof(regk_result, json_total),
                offsetof(regk_result, opaque), sizeof(regk_gather), offsetof(regk_gather, totals),
@@ -60,6 +62,8 @@ def test_struct_layouts_match_header(built):
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
     got = [C.sizeof(_native.CParents), _native.CParents.unique_first.offset, _native.CParents.kernel_ms.offset,
+           C.sizeof(_native.CJob), _native.CJob.mailbox.offset, _native.CJob.timeout_ms.offset,
+           _native.CResult.job_path_base.offset, _native.CResult.job_json_total.offset,
            C.sizeof(_native.CBatch), _native.CBatch.domain_bytes.offset, _native.CBatch.ports_present.offset,
            C.sizeof(_native.CResult), _native.CResult.json_total.offset, _native.CResult.opaque.offset,
            C.sizeof(_native.CGather), _native.CGather.totals.offset, _native.CGather.json_off.offset,
