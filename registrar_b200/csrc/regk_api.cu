@@ -909,9 +909,9 @@ static void fill_peers(PeerDst &pd, const regk_job &j, void *const *bytes, uint6
 {
     pd.n = 0;
     pd.job = 1;
-    for (uint32_t q = 0; q < j.world; q++) {
-        if (q == j.rank)
-            continue;
+    /* destination order rank+1, rank+2, ...: at any moment the ranks aim at different peers */
+    for (uint32_t i = 1; i < j.world; i++) {
+        const uint32_t q = (j.rank + i) % j.world;
         pd.bytes[pd.n] = (uint8_t *)bytes[q];
         pd.off[pd.n] = (unsigned long long *)off[q] + j.rec_base;
         pd.n++;

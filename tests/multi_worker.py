@@ -6,6 +6,8 @@ from registrar_b200 import _native, synth, multigpu
 from registrar_b200.batch import FLAG_OUT_DEVICE
 from oracle import oracle
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+def say(*words):                                     # one write per line: the ranks share a pipe
+    sys.stdout.write("RANK %d %s\n" % (rank, " ".join(words))); sys.stdout.flush()
 torch.cuda.set_device(rank)
 dev = torch.device("cuda", rank)
 dist.init_process_group("nccl", device_id=dev)
@@ -39,7 +41,7 @@ ok2 = (np.array_equal(g2.path_bytes.cpu().numpy(), whole.path_bytes) and np.arra
        and np.array_equal(g2.json_off.cpu().numpy().astype(np.uint64), whole.json_off)
        and g2.nbytes_received == g.nbytes_received)
 pg.close()
-print("RANK", rank, "PEER", "OK" if ok2 else "MISMATCH", flush=True)
+say("PEER", "OK" if ok2 else "MISMATCH")
 ok = ok and ok2
 # the product path: all-gather fused into the compose kernels (REGK_JOB_STEP), no collective on the data path
 def same(g):
@@ -59,7 +61,7 @@ for variant in ("shared", "shared-again", "generic", "tiny-tiles"):
     good = same(g3) and int(r3.path_total) == int(res.path_total) and int(r3.json_total) == int(res.json_total) \
         and g3.nbytes_received == g.nbytes_received and int(r3.job_path_total) == int(whole.path_off[-1]) \
         and int(r3.job_json_total) == int(whole.json_off[-1])
-    print("RANK", rank, "JOB", variant, "OK" if good else "MISMATCH", flush=True)
+    say("JOB", variant, "OK" if good else "MISMATCH")
     ok3 = ok3 and good
 ctx.set_option("force_generic", 0); ctx.set_option("dom_cap", 0)
 # async: two steps enqueued back to back, finished in order
@@ -68,7 +70,7 @@ t1 = job.step(dcb); t2 = job.step(dcb)
 ctx.finish(t1); r4 = ctx.finish(t2)
 ctx.set_option("async", 0)
 good = same(job.result(r4))
-print("RANK", rank, "JOB", "async", "OK" if good else "MISMATCH", flush=True)
+say("JOB", "async", "OK" if good else "MISMATCH")
 ok3 = ok3 and good
 # a shard with an empty label cannot be placed in closed form: refused, not wrong
 recs = [shard.record(i) for i in range(300)]
@@ -84,11 +86,11 @@ try:
 except _native.RegkError as e:
     refused = e.code == _native.REGK_ERR_STATE
 good = refused == (rank == 1)
-print("RANK", rank, "JOB", "empty-label", "OK" if good else "MISMATCH", flush=True)
+say("JOB", "empty-label", "OK" if good else "MISMATCH")
 ok3 = ok3 and good
 job2.close()
 job.close()
 ok = ok and ok3
-print("RANK", rank, "OK" if ok else "MISMATCH", flush=True)
+say("ALL", "OK" if ok else "MISMATCH")
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

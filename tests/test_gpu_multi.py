@@ -23,5 +23,6 @@ def test_two_rank_gather_equals_single_stream(built, tmp_path):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-8000:]
     assert out.stdout.count("PEER OK") == 2, out.stdout[-2000:]
+    assert out.stdout.count("ALL OK") == 2, out.stdout[-2000:]
     for variant in ("shared", "shared-again", "generic", "tiny-tiles", "async", "empty-label"):
         assert out.stdout.count("JOB %s OK" % variant) == 2, out.stdout[-3000:]

@@ -298,7 +298,7 @@ def _random_records(rng, n, shape):
         rec = {"domain": b".".join(labels), "hostname": host, "type": [b"host", b"load_balancer", b"redis_host"][int(rng.integers(0, 3))],
                "address": word(1, shape["addr_hi"])}
         if rng.random() < 0.6:
-            rec["ttl"] = int(rng.choice([0, 5, 30, 86400, 2147483647, -1, -2147483648, int(rng.integers(0, 10 ** 9))]))
+            rec["ttl"] = int(rng.choice([0, 5, 30, 86400, 2147483647, -1, -2147483647, int(rng.integers(0, 10 ** 9))]))
         if rng.random() < 0.5:
             rec["ports"] = [int(x) for x in rng.integers(0, 70000, int(rng.integers(0, 5)))]
         recs.append(rec)
