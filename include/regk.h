@@ -64,6 +64,8 @@ extern "C" {
                                             outside 0x20..0x7f or needing a JSON escape (" or \) */
 #define REGK_BAD_TYPE_ID      (1u << 3)  /* type_id >= number of types set */
 #define REGK_BAD_TOO_LARGE    (1u << 4)  /* a single record's path or payload exceeds 2^31 bytes */
+#define REGK_BAD_SERVICE_BYTE (1u << 5)  /* service records: srvce / proto byte outside 0x20..0x7f or needing a JSON escape */
+#define REGK_BAD_KEY_ORDER    (1u << 6)  /* service records: key_order is not a permutation of the four members */
 
 #define REGK_TTL_ABSENT  INT32_MIN      /* registration.ttl === undefined -> key omitted (register.js:144) */
 
@@ -162,6 +164,36 @@ int         regk_register_batch(regk_ctx *ctx, const regk_batch *batch, regk_res
    fills totals / validation / timings and returns its status.  (Synchronous mode calls it itself.) */
 int         regk_finish(regk_ctx *ctx, regk_result *result);
 int         regk_release(regk_ctx *ctx, regk_result *result);
+
+/*
+ * ---- service records (reference lib/register.js:45-75 registerService) ------------------------------------------
+ * The persistent node a registration with `registration.service` also writes: zk.put(domainToPath(domain),
+ * { type: 'service', service: registration.service }) with registration.service = { type: 'service', service:
+ * { srvce, proto, port, ttl } } (asserted at :186-199, ttl defaulted to 60 at :197).  Payload bytes (zkplus ->
+ * JSON.stringify, insertion order):
+ *   {"type":"service","service":{"type":"service","service":{<srvce, proto, port, ttl in the CALLER's key order>}}}
+ * The node's PATH is an alias-mode path (regk_register_batch with REGK_NODE_ALIAS | REGK_NO_JSON).
+ * key_order[i]: four 2-bit key ids, first member in bits 0-1 (0 srvce, 1 proto, 2 port, 3 ttl); NULL = that order.
+ * A ttl the caller left undefined is appended last by the reference's assignment: the host layer passes the
+ * defaulted value and an order that ends in ttl.  Fence: REGK_BAD_SERVICE_BYTE, REGK_BAD_KEY_ORDER,
+ * REGK_BAD_TOO_LARGE (offsets); port is uint32, ttl int32.  Only json_bytes / json_off / json_total of the result
+ * are filled.  Synchronous; honours REGK_IN_DEVICE / REGK_OUT_DEVICE.
+ */
+typedef struct regk_service_batch {
+    uint64_t        n;
+    uint32_t        flags;
+    uint32_t        reserved;
+    uint64_t        srvce_bytes_len, proto_bytes_len;   /* required for device batches */
+    const uint8_t  *srvce_bytes;    /* registration.service.service.srvce per record, packed ("_http") */
+    const uint32_t *srvce_off;      /* [n+1] */
+    const uint8_t  *proto_bytes;    /* ....proto ("_tcp") */
+    const uint32_t *proto_off;      /* [n+1] */
+    const uint32_t *port;           /* [n] */
+    const int32_t  *ttl;            /* [n] (already defaulted) */
+    const uint8_t  *key_order;      /* [n] or NULL */
+} regk_service_batch;
+
+int         regk_service_records(regk_ctx *ctx, const regk_service_batch *batch, regk_result *result);
 
 /* Pinned host memory for callers that want zero-staging H2D/D2H. */
 void       *regk_host_alloc(regk_ctx *ctx, size_t bytes);
@@ -268,6 +300,88 @@ typedef struct regk_parents {
 } regk_parents;
 
 int         regk_parent_dirs(regk_ctx *ctx, uint32_t flags, regk_parents *out);
+
+/*
+ * ---- ZooKeeper wire framing of a batch (reference lib/register.js:156-159: zk.create(n, _obj, {flags:
+ * ['ephemeral_plus']}) -> zkplus -> one jute CreateRequest per node on the socket) -----------------------------------
+ * Works on the batch most recently finished on this context (paths AND payloads; its device copies are still in
+ * the context): frame i = 4-byte big-endian length | RequestHeader{xid = xid_base + i, type = 1 (create)} |
+ * CreateRequest{path, data = payload i, acl = [OPEN_ACL_UNSAFE: perms 31, "world", "anyone"], flags = zk_flags}
+ * (1 = EPHEMERAL for host records, 0 = persistent for service records).  frame_off[i] = path_off[i] + json_off[i]
+ * + 51 i.  PARITY UNPINNED: zkplus / ZooKeeper are not in the reference tree (package.json:20); the layout follows
+ * the published zookeeper.jute definitions and is tested against an independent restatement, not against a server.
+ * flags: REGK_OUT_DEVICE returns device pointers, else pinned host arrays; valid until the next call.
+ */
+typedef struct regk_frames {
+    uint64_t n;
+    uint64_t total;                 /* == frame_off[n] */
+    uint32_t flags;
+    uint32_t launches;
+    const uint8_t *frame_bytes;
+    const uint64_t *frame_off;      /* [n+1] */
+    float kernel_ms;
+} regk_frames;
+
+int         regk_jute_frames(regk_ctx *ctx, uint32_t flags, int32_t xid_base, uint32_t zk_flags, regk_frames *out);
+
+/*
+ * ---- the reader side: decode paths and payloads back into records (README.md:462-480, :587-664) -----------------
+ * Inverse of regk_register_batch / regk_service_records for audits of registry contents and round-trip checks:
+ *   path    -> domain (labels reversed back, '/' -> '.'); for host nodes the last component is the instance name
+ *              (lib/register.js:221-223) and is reported as (host_pos, host_len) inside the path
+ *   payload -> type, address (positions inside the payload), ttl, ports - for the canonical compact form
+ *              {"type":T,"address":A[,"ttl":n],T:{"address":A[,"ports":[..]]}} ; service records
+ *              {"type":"service","service":{"type":"service","service":{srvce,proto,port,ttl in any order}}} come
+ *              back with type_* = srvce, addr_* = proto, ports[0] = port.
+ * Input: explicit streams (host, or device with REGK_IN_DEVICE; 64-bit CSR offsets as in regk_result), or
+ * REGK_DECODE_LAST = the batch finished last on this context.  Either stream may be NULL.
+ * Output: rec[n]; domains in SLOT layout (domain i = dom_bytes[path_off[i], + rec[i].dom_len)); ports in slot layout
+ * (record i's ports = ports[json_off[i] / 2, + rec[i].nports)).  REGK_OUT_DEVICE returns device pointers.
+ */
+#define REGK_DECODE_LAST       (1u << 8)
+
+#define REGK_DEC_PATH_OK        (1u << 0)
+#define REGK_DEC_HOST_RECORD    (1u << 1)
+#define REGK_DEC_SERVICE_RECORD (1u << 2)
+#define REGK_DEC_NOT_CANONICAL  (1u << 3)   /* not the compact form this library writes */
+#define REGK_DEC_KEY_MISMATCH   (1u << 4)   /* the inner object's name differs from the value of "type" (README.md:596) */
+#define REGK_DEC_ADDR_MISMATCH  (1u << 5)   /* the two "address" members differ */
+#define REGK_DEC_BAD_NUMBER     (1u << 6)   /* ttl / port not an integer in range */
+#define REGK_DEC_BAD_PATH       (1u << 7)   /* no leading '/', or a host node without an instance name */
+
+typedef struct regk_decoded {
+    uint32_t flags;                 /* REGK_DEC_* */
+    uint32_t dom_len;
+    uint32_t host_pos, host_len;    /* instance name inside the path (host nodes) */
+    uint32_t type_pos, type_len;    /* inside the payload (JSON escapes left as they are) */
+    uint32_t addr_pos, addr_len;
+    int32_t  ttl;                   /* REGK_TTL_ABSENT when the key is missing */
+    uint32_t nports;                /* 0xFFFFFFFF when the key is missing */
+} regk_decoded;
+
+typedef struct regk_decode_in {
+    uint64_t n;
+    uint32_t flags;                 /* REGK_IN_DEVICE | REGK_OUT_DEVICE | REGK_DECODE_LAST */
+    uint32_t host_nodes;            /* != 0: paths are host nodes (domain path + '/' + instance name) */
+    uint64_t path_total, json_total;    /* required for device streams */
+    const uint8_t *path_bytes;
+    const uint64_t *path_off;       /* [n+1] */
+    const uint8_t *json_bytes;
+    const uint64_t *json_off;       /* [n+1] */
+} regk_decode_in;
+
+typedef struct regk_decode_out {
+    uint64_t n;
+    uint32_t flags;
+    uint32_t launches;
+    const regk_decoded *rec;        /* [n] */
+    const uint8_t *dom_bytes;       /* [path_total] slot layout */
+    const uint32_t *ports;          /* [json_total / 2 + 1] slot layout */
+    uint64_t dom_bytes_len, ports_len;
+    float kernel_ms;
+} regk_decode_out;
+
+int         regk_decode(regk_ctx *ctx, const regk_decode_in *in, regk_decode_out *out);
 
 /* Tuning knobs (kernel variant selection for A/B measurement); see DESIGN.md. */
 int         regk_set_option(regk_ctx *ctx, const char *name, int64_t value);

@@ -48,7 +48,7 @@ def lib():
         _LIB = C.CDLL(build())
         for name in ("ro_domain_to_path", "ro_posix_normalize", "ro_posix_join2", "ro_posix_dirname",
                      "ro_host_node_path", "ro_quote_json_string", "ro_host_record_json", "ro_path_len",
-                     "ro_json_len"):
+                     "ro_json_len", "ro_service_json"):
             getattr(_LIB, name).restype = C.c_size_t
         _LIB.ro_register_batch.restype = C.c_uint32
         _LIB.ro_validate_record.restype = C.c_uint32
@@ -106,6 +106,28 @@ def host_record_json(type_: bytes, address: bytes, ttl=None, ports=None) -> byte
                                   C.c_int(ttl is not None), C.c_int32(0 if ttl is None else ttl),
                                   C.c_int(ports is not None), arr, C.c_size_t(k), out)
     return bytes(out[:n])
+
+
+def service_json(srvce: bytes, proto: bytes, port: int, ttl: int, order=(0, 1, 2, 3)) -> bytes:
+    """Payload of the service record (lib/register.js:58-62); order = the inner object's key order."""
+    out = _buf(160 + 6 * (len(srvce) + len(proto)))
+    o = (C.c_uint8 * 4)(*order)
+    n = lib().ro_service_json(srvce, C.c_size_t(len(srvce)), proto, C.c_size_t(len(proto)), C.c_int64(port),
+                              C.c_int64(ttl), o, out)
+    return bytes(out[:n])
+
+
+def service_batch(sb):
+    """The C oracle over a registrar_b200.batch.ServiceBatch: (payload bytes, offsets)."""
+    outs, off = [], np.zeros(sb.n + 1, np.uint64)
+    for i in range(sb.n):
+        ko = int(sb.key_order[i]) if sb.key_order is not None else 0xE4
+        order = [(ko >> (2 * j)) & 3 for j in range(4)]
+        outs.append(service_json(bytes(sb.srvce_bytes[sb.srvce_off[i]:sb.srvce_off[i + 1]]),
+                                 bytes(sb.proto_bytes[sb.proto_off[i]:sb.proto_off[i + 1]]),
+                                 int(sb.port[i]), int(sb.ttl[i]), order))
+        off[i + 1] = off[i] + np.uint64(len(outs[-1]))
+    return np.frombuffer(b"".join(outs), np.uint8), off
 
 
 def _ptr(a):

@@ -111,3 +111,45 @@ def register_record(rec: dict, alias: bool = False):
     addr = dec(rec.get("address", rec.get("adminIp", "")))
     payload = host_record_json(dec(rec["type"]), addr, rec.get("ttl"), rec.get("ports"))
     return path.encode("utf-8"), payload
+
+
+# --------------------------------------------------------------------------- wire framing
+def jute_create_request(path: bytes, data: bytes, xid: int, flags: int = 1) -> bytes:
+    """One ZooKeeper CreateRequest frame as zkplus would put it on the socket for zk.create(path, obj,
+    {flags:['ephemeral_plus']}) (lib/register.js:156-159).  PARITY UNPINNED: zkplus / ZooKeeper are not in the
+    reference tree; this follows the published zookeeper.jute definitions (RequestHeader{int xid; int type},
+    CreateRequest{ustring path; buffer data; vector<ACL> acl; int flags}, ACL{int perms; Id{ustring scheme;
+    ustring id}}; big-endian ints, length-prefixed strings/buffers; OpCode.create = 1; OPEN_ACL_UNSAFE)."""
+    import struct
+    body = struct.pack(">i", xid) + struct.pack(">i", 1)
+    body += struct.pack(">i", len(path)) + path
+    body += struct.pack(">i", len(data)) + data
+    body += struct.pack(">i", 1)                                    # one ACL
+    body += struct.pack(">i", 31)                                   # Perms.ALL
+    body += struct.pack(">i", 5) + b"world" + struct.pack(">i", 6) + b"anyone"
+    body += struct.pack(">i", flags)
+    return struct.pack(">i", len(body)) + body
+
+
+# --------------------------------------------------------------------------------- reader side (§8f-4)
+def path_to_domain(path: str, host_node: bool):
+    """(domain, instance name) - inverse of domain_to_path / host_node_path for paths this library writes."""
+    assert path.startswith("/")
+    host = None
+    if host_node:
+        path, _, host = path.rpartition("/")
+        if path == "":
+            path = "/"
+    comps = path[1:].split("/") if len(path) > 1 else []
+    return ".".join(reversed(comps)), host
+
+
+def decode_payload(payload: bytes):
+    """json.loads view of a payload: {'kind': 'host'|'service', type, address, ttl, ports} (None = key absent)."""
+    obj = json.loads(payload.decode("utf-8"), object_pairs_hook=OrderedDict)
+    if obj.get("type") == "service" and "service" in obj:
+        inner = obj["service"]["service"]
+        return {"kind": "service", "type": inner["srvce"], "address": inner["proto"], "ttl": inner.get("ttl"),
+                "ports": [inner["port"]]}
+    t = obj["type"]
+    return {"kind": "host", "type": t, "address": obj["address"], "ttl": obj.get("ttl"), "ports": obj[t].get("ports")}

@@ -307,6 +307,43 @@ RO_EXPORT size_t ro_host_record_json(const uint8_t *type, size_t tl, const uint8
 }
 
 /* ------------------------------------------------------------------------
+ * Service record (lib/register.js:45-75): zk.put(p, {type:'service', service: registration.service}) with
+ * registration.service = {type:'service', service:{srvce, proto, port, ttl}} (asserts :186-199, ttl default :197).
+ * `order` lists the four members of the inner object in the caller's insertion order (0 srvce, 1 proto, 2 port,
+ * 3 ttl); strings are escaped per ECMA-262, numbers are integers here.  out needs 160 + 6*(sl+pl) bytes.
+ * ---------------------------------------------------------------------- */
+RO_EXPORT size_t ro_service_json(const uint8_t *srvce, size_t sl, const uint8_t *proto, size_t pl, int64_t port,
+    int64_t ttl, const uint8_t *order, uint8_t *out)
+{
+    size_t o = 0;
+    o += ro_lit(out + o, "{\"type\":\"service\",\"service\":{\"type\":\"service\",\"service\":{");
+    for (int i = 0; i < 4; i++) {
+        if (i)
+            out[o++] = ',';
+        switch (order[i]) {
+        case 0:
+            o += ro_lit(out + o, "\"srvce\":");
+            o += ro_quote_json_string(srvce, sl, out + o);
+            break;
+        case 1:
+            o += ro_lit(out + o, "\"proto\":");
+            o += ro_quote_json_string(proto, pl, out + o);
+            break;
+        case 2:
+            o += ro_lit(out + o, "\"port\":");
+            o += ro_i64_dec(port, out + o);
+            break;
+        default:
+            o += ro_lit(out + o, "\"ttl\":");
+            o += ro_i64_dec(ttl, out + o);
+            break;
+        }
+    }
+    o += ro_lit(out + o, "}}}");
+    return o;
+}
+
+/* ------------------------------------------------------------------------
  * Input-domain fence (include/regk.h REGK_BAD_*): the same predicate the GPU
  * path evaluates per record.
  * ---------------------------------------------------------------------- */

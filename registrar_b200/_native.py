@@ -74,6 +74,39 @@ class CGather(C.Structure):          # regk_gather
                 ("path_cap", C.c_uint64), ("json_cap", C.c_uint64)]
 
 
+class CServiceBatch(C.Structure):    # regk_service_batch
+    _fields_ = [("n", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("srvce_bytes_len", C.c_uint64), ("proto_bytes_len", C.c_uint64),
+                ("srvce_bytes", C.c_void_p), ("srvce_off", C.c_void_p),
+                ("proto_bytes", C.c_void_p), ("proto_off", C.c_void_p),
+                ("port", C.c_void_p), ("ttl", C.c_void_p), ("key_order", C.c_void_p)]
+
+
+class CFrames(C.Structure):          # regk_frames
+    _fields_ = [("n", C.c_uint64), ("total", C.c_uint64), ("flags", C.c_uint32), ("launches", C.c_uint32),
+                ("frame_bytes", C.c_void_p), ("frame_off", C.c_void_p), ("kernel_ms", C.c_float)]
+
+
+class CDecodeIn(C.Structure):        # regk_decode_in
+    _fields_ = [("n", C.c_uint64), ("flags", C.c_uint32), ("host_nodes", C.c_uint32),
+                ("path_total", C.c_uint64), ("json_total", C.c_uint64),
+                ("path_bytes", C.c_void_p), ("path_off", C.c_void_p), ("json_bytes", C.c_void_p), ("json_off", C.c_void_p)]
+
+
+class CDecodeOut(C.Structure):       # regk_decode_out
+    _fields_ = [("n", C.c_uint64), ("flags", C.c_uint32), ("launches", C.c_uint32),
+                ("rec", C.c_void_p), ("dom_bytes", C.c_void_p), ("ports", C.c_void_p),
+                ("dom_bytes_len", C.c_uint64), ("ports_len", C.c_uint64), ("kernel_ms", C.c_float)]
+
+
+# regk_decoded as a NumPy record type
+DECODED_DTYPE = np.dtype([("flags", "<u4"), ("dom_len", "<u4"), ("host_pos", "<u4"), ("host_len", "<u4"),
+                          ("type_pos", "<u4"), ("type_len", "<u4"), ("addr_pos", "<u4"), ("addr_len", "<u4"),
+                          ("ttl", "<i4"), ("nports", "<u4")])
+FLAG_DECODE_LAST = 1 << 8
+DEC_PATH_OK, DEC_HOST_RECORD, DEC_SERVICE_RECORD, DEC_NOT_CANONICAL = 1, 2, 4, 8
+DEC_KEY_MISMATCH, DEC_ADDR_MISMATCH, DEC_BAD_NUMBER, DEC_BAD_PATH = 16, 32, 64, 128
+
 MAILBOX_BYTES = MAX_PEERS * 32
 
 
@@ -94,7 +127,8 @@ EXPORTS = ["regk_abi_version", "regk_create", "regk_destroy", "regk_last_error",
            "regk_set_types", "regk_register_batch", "regk_finish", "regk_release", "regk_host_alloc",
            "regk_host_free", "regk_dev_alloc", "regk_dev_free", "regk_memcpy_h2d", "regk_memcpy_d2h",
            "regk_sync", "regk_set_option", "regk_get_option", "regk_ipc_export", "regk_ipc_open", "regk_ipc_close",
-           "regk_gather_push", "regk_parent_dirs", "regk_job_bind"]
+           "regk_gather_push", "regk_parent_dirs", "regk_job_bind", "regk_service_records",
+           "regk_jute_frames", "regk_decode"]
 
 _lib = None
 
@@ -141,6 +175,9 @@ def load_library():
     lib.regk_gather_push.argtypes = [vp, C.POINTER(CResult), C.POINTER(CGather)]
     lib.regk_parent_dirs.argtypes = [vp, u32, C.POINTER(CParents)]
     lib.regk_job_bind.argtypes = [vp, C.POINTER(CJob)]
+    lib.regk_service_records.argtypes = [vp, C.POINTER(CServiceBatch), C.POINTER(CResult)]
+    lib.regk_jute_frames.argtypes = [vp, u32, C.c_int32, u32, C.POINTER(CFrames)]
+    lib.regk_decode.argtypes = [vp, C.POINTER(CDecodeIn), C.POINTER(CDecodeOut)]
     _lib = lib
     return lib
 
@@ -289,6 +326,64 @@ class Context:
             float(res.json_len_kernel_ms))
         self._lib.regk_release(self._h, C.byref(res))
         return out
+
+    # -- service records (lib/register.js:45-75), host buffers in / host buffers out --
+    def service_records(self, sb) -> HostResult:
+        """ServiceBatch -> payloads of the persistent service nodes (only json_* of the result are filled)."""
+        keep = [None if x is None else np.ascontiguousarray(x) for x in (
+            sb.srvce_bytes, sb.srvce_off, sb.proto_bytes, sb.proto_off, sb.port, sb.ttl, sb.key_order)]
+        n = sb.n
+        cb = CServiceBatch(n=n, flags=0, srvce_bytes_len=int(sb.srvce_off[-1]) if n else 0,
+                           proto_bytes_len=int(sb.proto_off[-1]) if n else 0,
+                           srvce_bytes=_np_ptr(keep[0]), srvce_off=_np_ptr(keep[1]), proto_bytes=_np_ptr(keep[2]),
+                           proto_off=_np_ptr(keep[3]), port=_np_ptr(keep[4]), ttl=_np_ptr(keep[5]),
+                           key_order=_np_ptr(keep[6]))
+        res = CResult()
+        rc = self._lib.regk_service_records(self._h, C.byref(cb), C.byref(res))
+        del keep
+        if rc != REGK_OK:
+            self._check(rc, res)
+        out = HostResult(n, np.zeros(0, np.uint8), np.zeros(n + 1, np.uint64),
+                         _as_np(res.json_bytes, int(res.json_total), np.uint8).copy(),
+                         _as_np(res.json_off, n + 1, np.uint64).copy(), float(res.kernel_ms), 0.0,
+                         float(res.json_kernel_ms), int(res.launches))
+        self._lib.regk_release(self._h, C.byref(res))
+        return out
+
+    # -- ZooKeeper wire frames of the batch finished last (lib/register.js:156-159 -> zkplus -> jute) --
+    def jute_frames(self, xid_base: int = 1, zk_flags: int = 1, device: bool = False):
+        """(frame_bytes uint8[total], frame_off uint64[n+1], kernel_ms): one CreateRequest per record of the batch
+        finished last on this context.  device=True returns the raw CFrames (device pointers)."""
+        out = CFrames()
+        self._check(self._lib.regk_jute_frames(self._h, FLAG_OUT_DEVICE if device else 0, int(xid_base), int(zk_flags),
+                                               C.byref(out)))
+        if device:
+            return out
+        n = int(out.n)
+        return (_as_np(out.frame_bytes, int(out.total), np.uint8).copy(), _as_np(out.frame_off, n + 1, np.uint64).copy(),
+                float(out.kernel_ms))
+
+    # -- the reader side: paths and payloads back into records --
+    def decode(self, path_bytes=None, path_off=None, json_bytes=None, json_off=None, host_nodes: bool = True,
+               last: bool = False):
+        """regk_decode over explicit host streams (uint8 bytes + uint64 CSR offsets) or, with last=True, over the
+        batch finished last on this context.  Returns (rec: structured array of regk_decoded, dom_bytes in slot
+        layout, ports in slot layout, kernel_ms)."""
+        keep = [None if a is None else np.ascontiguousarray(a) for a in (path_bytes, path_off, json_bytes, json_off)]
+        n = 0
+        for off in (keep[1], keep[3]):
+            if off is not None:
+                n = len(off) - 1
+        cin = CDecodeIn(n=n, flags=FLAG_DECODE_LAST if last else 0, host_nodes=1 if host_nodes else 0,
+                        path_bytes=_np_ptr(keep[0]), path_off=_np_ptr(keep[1]), json_bytes=_np_ptr(keep[2]),
+                        json_off=_np_ptr(keep[3]))
+        out = CDecodeOut()
+        self._check(self._lib.regk_decode(self._h, C.byref(cin), C.byref(out)))
+        n = int(out.n)
+        rec = np.frombuffer((C.c_uint8 * (n * DECODED_DTYPE.itemsize)).from_address(out.rec), dtype=DECODED_DTYPE,
+                            count=n).copy() if n else np.zeros(0, DECODED_DTYPE)
+        return (rec, _as_np(out.dom_bytes, int(out.dom_bytes_len), np.uint8).copy(),
+                _as_np(out.ports, int(out.ports_len), np.uint32).copy(), float(out.kernel_ms))
 
     # -- two-deep submission of host batches: the next batch's H2D overlaps this batch's result traffic --
     def submit(self, batch: RecordBatch, paths: bool = True, payloads: bool = True):

@@ -30,6 +30,8 @@ BAD_HOST_BYTE = 1 << 1
 BAD_ADDR_BYTE = 1 << 2
 BAD_TYPE_ID = 1 << 3
 BAD_TOO_LARGE = 1 << 4
+BAD_SERVICE_BYTE = 1 << 5
+BAD_KEY_ORDER = 1 << 6
 
 
 def _pack(strings: Sequence[bytes]):
@@ -195,3 +197,52 @@ class RecordBatch:
             if a is not None:
                 tot += a.nbytes
         return tot
+
+
+SERVICE_KEYS = ("srvce", "proto", "port", "ttl")      # key ids 0..3 of regk_service_batch.key_order
+
+
+@dataclass
+class ServiceBatch:
+    """Struct-of-arrays image of ``regk_service_batch``: one `registration.service` object per record
+    (reference lib/register.js:186-199; the record written at :58-62)."""
+    n: int
+    srvce_bytes: np.ndarray
+    srvce_off: np.ndarray
+    proto_bytes: np.ndarray
+    proto_off: np.ndarray
+    port: np.ndarray
+    ttl: np.ndarray
+    key_order: Optional[np.ndarray] = None
+
+    @classmethod
+    def from_services(cls, services: Iterable[dict]) -> "ServiceBatch":
+        """services: the callers' `registration.service` objects, {"type": "service", "service": {srvce, proto,
+        port, ttl?}}.  The inner object's key order is kept (JSON.stringify follows insertion order); a missing
+        ttl is defaulted to 60 and goes LAST, exactly what the assignment at lib/register.js:197 does."""
+        services = list(services)
+        srv, pro, ports, ttls, orders = [], [], [], [], []
+        for i, s in enumerate(services):
+            if list(s.keys()) != ["type", "service"] or s["type"] != "service":
+                raise ValueError("service %d: expected {type: 'service', service: {...}} in that key order" % i)
+            inner = s["service"]
+            keys = list(inner.keys())
+            extra = [k for k in keys if k not in SERVICE_KEYS]
+            if extra:
+                raise ValueError("service %d: members %r are outside the supported input domain" % (i, extra))
+            for k in ("srvce", "proto", "port"):
+                if k not in inner:
+                    raise ValueError("service %d: %s is required" % (i, k))
+            ttl = inner.get("ttl")
+            if ttl is None:
+                keys = [k for k in keys if k != "ttl"] + ["ttl"]
+                ttl = 60
+            srv.append(_b(inner["srvce"]))
+            pro.append(_b(inner["proto"]))
+            ports.append(_integral(inner["port"], 0, 2 ** 32 - 1, "service port"))
+            ttls.append(_integral(ttl, -(2 ** 31), 2 ** 31 - 1, "service ttl"))
+            orders.append(sum(SERVICE_KEYS.index(k) << (2 * j) for j, k in enumerate(keys)))
+        sb, so = _pack(srv)
+        pb, po = _pack(pro)
+        return cls(n=len(services), srvce_bytes=sb, srvce_off=so, proto_bytes=pb, proto_off=po,
+                   port=np.array(ports, np.uint32), ttl=np.array(ttls, np.int32), key_order=np.array(orders, np.uint8))

@@ -22,6 +22,9 @@
 #include "regk_kernels.cuh"
 #include "regk_gather.cuh"
 #include "regk_peersync.cuh"
+#include "regk_service.cuh"
+#include "regk_jute.cuh"
+#include "regk_decode.cuh"
 #include "regk_parents.cuh"
 #include "regk_types.hpp"
 
@@ -87,9 +90,18 @@ struct regk_ctx {
     const uint8_t *last_path_bytes = nullptr;
     const unsigned long long *last_path_off = nullptr;
     uint64_t last_n = 0;
+    /* ... and of its payload stream (regk_jute_frames / regk_decode work on both) */
+    const uint8_t *last_json_bytes = nullptr;
+    const unsigned long long *last_json_off = nullptr;
+    uint64_t last_json_n = 0;
+    DevBuf jute_bytes, jute_off;
+    HostBuf h_jute_bytes, h_jute_off;
+    DevBuf dec_in[4], dec_rec, dec_dom, dec_ports;
+    HostBuf h_dec_rec, h_dec_dom, h_dec_ports;
     const uint32_t *last_host_off = nullptr;
     uint32_t last_host_stride = 0;
     bool last_alias = false;
+    DevBuf svc_in[7], svc_work;                 /* regk_service_records: staged inputs, status + tile totals */
     DevBuf par_len, par_slot, par_table, par_totals, par_unique;
     cudaEvent_t par_ev[2] = {nullptr, nullptr};
     HostBuf h_par_len, h_par_unique, h_par_count;
@@ -121,6 +133,8 @@ struct regk_ctx {
         bool timed = true;                      /* ev[0..2] were recorded for this batch */
         const uint8_t *dev_path_bytes = nullptr;        /* where this batch's path stream lives on the device */
         const unsigned long long *dev_path_off = nullptr;
+        const uint8_t *dev_json_bytes = nullptr;
+        const unsigned long long *dev_json_off = nullptr;
         const uint32_t *dev_host_off = nullptr;         /* how its paths end: hostname lengths (NULL: fixed stride) */
         uint32_t host_stride = 0;
         bool alias = false;
@@ -217,7 +231,7 @@ size_t align16(size_t v)
 bool smem_attr_needs_raise(int device, int which, size_t bytes)
 {
     static std::mutex mu;
-    static size_t high[64][3];
+    static size_t high[64][4];
     std::lock_guard<std::mutex> lock(mu);
     size_t &h = high[device & 63][which];
     if (bytes <= h)
@@ -615,9 +629,22 @@ void regk_destroy(regk_ctx *ctx)
         cudaFreeHost(ctx->h_job_bases);
     if (ctx->job_bases.p)
         cudaFree(ctx->job_bases.p);
-    for (DevBuf *b : {&ctx->par_len, &ctx->par_slot, &ctx->par_table, &ctx->par_totals, &ctx->par_unique})
+    for (auto &b : ctx->dec_in)
+        if (b.p)
+            cudaFree(b.p);
+    for (DevBuf *b : {&ctx->dec_rec, &ctx->dec_dom, &ctx->dec_ports})
         if (b->p)
             cudaFree(b->p);
+    for (HostBuf *b : {&ctx->h_jute_bytes, &ctx->h_jute_off, &ctx->h_dec_rec, &ctx->h_dec_dom, &ctx->h_dec_ports})
+        if (b->p)
+            cudaFreeHost(b->p);
+    for (DevBuf *b : {&ctx->par_len, &ctx->par_slot, &ctx->par_table, &ctx->par_totals, &ctx->par_unique, &ctx->svc_work,
+             &ctx->jute_bytes, &ctx->jute_off})
+        if (b->p)
+            cudaFree(b->p);
+    for (auto &b : ctx->svc_in)
+        if (b.p)
+            cudaFree(b.p);
     for (auto &ev : ctx->par_ev)
         if (ev)
             cudaEventDestroy(ev);
@@ -1223,6 +1250,9 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
             ctx->last_path_bytes = do_path ? pp.out_bytes : nullptr;
             ctx->last_path_off = do_path ? pp.out_off : nullptr;
             ctx->last_n = do_path ? n : 0;
+            ctx->last_json_bytes = do_json ? jp.out_bytes : nullptr;
+            ctx->last_json_off = do_json ? jp.out_off : nullptr;
+            ctx->last_json_n = do_json ? n : 0;
             ctx->last_host_off = pp.host_off;
             ctx->last_host_stride = pp.host_stride;
             ctx->last_alias = alias;
@@ -1241,6 +1271,8 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     slot.d_status = d_status;
     slot.dev_path_bytes = (n && do_path && !job) ? pp.out_bytes : nullptr;    /* regk_parent_dirs: not on job steps */
     slot.dev_path_off = (n && do_path && !job) ? pp.out_off : nullptr;
+    slot.dev_json_bytes = (n && do_json && !job) ? jp.out_bytes : nullptr;
+    slot.dev_json_off = (n && do_json && !job) ? jp.out_off : nullptr;
     slot.dev_host_off = pp.host_off;
     slot.host_stride = pp.host_stride;
     slot.alias = alias;
@@ -1418,6 +1450,9 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     ctx->last_path_bytes = st.bad_bits ? nullptr : slot->dev_path_bytes;
     ctx->last_path_off = st.bad_bits ? nullptr : slot->dev_path_off;
     ctx->last_n = (st.bad_bits || !slot->dev_path_off) ? 0 : n;
+    ctx->last_json_bytes = st.bad_bits ? nullptr : slot->dev_json_bytes;
+    ctx->last_json_off = st.bad_bits ? nullptr : slot->dev_json_off;
+    ctx->last_json_n = (st.bad_bits || !slot->dev_json_off) ? 0 : n;
     ctx->last_host_off = slot->dev_host_off;
     ctx->last_host_stride = slot->host_stride;
     ctx->last_alias = slot->alias;
@@ -1503,6 +1538,342 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     res->path_off = (uint64_t *)ctx->h_path_off.p;
     res->json_bytes = (uint8_t *)ctx->h_json_bytes.p;
     res->json_off = (uint64_t *)ctx->h_json_off.p;
+    return REGK_OK;
+}
+
+int regk_service_records(regk_ctx *ctx, const regk_service_batch *b, regk_result *res)
+{
+    if (!ctx || !b || !res)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_service_records: NULL argument");
+    if (ctx->pending)
+        return fail(ctx, REGK_ERR_STATE, "regk_service_records: batches are still in flight; finish them first");
+    memset(res, 0, sizeof *res);
+    const uint64_t n = b->n;
+    const bool in_dev = b->flags & REGK_IN_DEVICE, out_dev = b->flags & REGK_OUT_DEVICE;
+    if (n >= (1ull << 32))
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_service_records: n must be < 2^32 per call");
+    if (n && (!b->srvce_off || !b->proto_off || !b->port || !b->ttl))
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_service_records: srvce_off / proto_off / port / ttl missing");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    uint64_t srvce_len = b->srvce_bytes_len, proto_len = b->proto_bytes_len;
+    if (!in_dev && n) {
+        srvce_len = b->srvce_off[n];
+        proto_len = b->proto_off[n];
+    }
+    if (n && ((srvce_len && !b->srvce_bytes) || (proto_len && !b->proto_bytes)))
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_service_records: string bytes missing");
+    const void *src[7] = {b->srvce_bytes, b->srvce_off, b->proto_bytes, b->proto_off, b->port, b->ttl, b->key_order};
+    const size_t sz[7] = {(size_t)srvce_len, (size_t)(n + 1) * 4, (size_t)proto_len, (size_t)(n + 1) * 4, (size_t)n * 4,
+        (size_t)n * 4, (size_t)n};
+    const void *dev[7];
+    int rc;
+    for (int i = 0; i < 7; i++) {
+        dev[i] = nullptr;
+        if (!src[i] || n == 0)
+            continue;
+        if (in_dev) {
+            if (((uintptr_t)src[i] & 15) != 0)
+                return fail(ctx, REGK_ERR_INVALID_ARG, "regk_service_records: device array %d is not 16-byte aligned", i);
+            dev[i] = src[i];
+        } else {
+            if ((rc = ensure_dev(ctx, ctx->svc_in[i], sz[i] + 16)))
+                return rc;
+            if (sz[i])
+                CK(cudaMemcpyAsync(ctx->svc_in[i].p, src[i], sz[i], cudaMemcpyHostToDevice, s));
+            dev[i] = ctx->svc_in[i].p;
+        }
+    }
+    /* 58 fixed + 3 commas + '}}}' + "srvce":"" + "proto":"" + "port": + 10 digits + "ttl": + '-' and 10 digits */
+    const uint64_t cap = n * (uint64_t)(58 + 3 + 3 + 10 + 10 + 7 + 10 + 6 + 11) + srvce_len + proto_len + 16;
+    const uint64_t ntiles = (n + TILE - 1) / TILE;
+    const size_t totals_off = 128, super_off = (totals_off + ntiles * 4 + 15) & ~(size_t)15;
+    const size_t work_bytes = super_off + (ntiles / SUPER + 1) * 8 + 64;
+    if ((rc = ensure_dev(ctx, ctx->json_bytes, cap)) || (rc = ensure_dev(ctx, ctx->json_off, (n + 1) * 8)) ||
+        (rc = ensure_dev(ctx, ctx->svc_work, work_bytes)))
+        return rc;
+    uint8_t *wk = (uint8_t *)ctx->svc_work.p;
+    CK(cudaMemsetAsync(wk, 0, work_bytes, s));
+    if (n == 0)
+        CK(cudaMemsetAsync(ctx->json_off.p, 0, 8, s));
+    regk_ctx::Slot &slot = ctx->slots[0];
+    uint32_t launches = 0;
+    if (n) {
+        ServiceParams p{};
+        p.n = n;
+        p.srvce_bytes = (const uint8_t *)dev[0];
+        p.srvce_off = (const uint32_t *)dev[1];
+        p.proto_bytes = (const uint8_t *)dev[2];
+        p.proto_off = (const uint32_t *)dev[3];
+        p.port = (const uint32_t *)dev[4];
+        p.ttl = (const int32_t *)dev[5];
+        p.key_order = (const uint8_t *)dev[6];
+        p.out_bytes = (uint8_t *)ctx->json_bytes.p;
+        p.out_off = (unsigned long long *)ctx->json_off.p;
+        p.out_capacity = cap;
+        p.tile_total = (uint32_t *)(wk + totals_off);
+        p.super_total = (unsigned long long *)(wk + super_off);
+        p.status = (DevStatus *)wk;
+        p.srvce_limit = srvce_len;
+        p.proto_limit = proto_len;
+        const uint64_t mean = 58 + 3 + 3 + 20 + 13 + 17 + (srvce_len + proto_len) / n + 2;
+        p.out_cap = (uint32_t)align16(std::min<uint64_t>(mean * TILE * 9 / 8 + 512, 98304));
+        const size_t smem = (size_t)p.out_cap + 32;
+        if (smem_attr_needs_raise(ctx->device, 3, smem))
+            CK(cudaFuncSetAttribute(regk_service_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaEventRecord(slot.ev[0], s));
+        regk_service_len_kernel<<<(unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * 8), TILE, 0, s>>>(p, (uint32_t)ntiles);
+        CK(cudaGetLastError());
+        regk_service_kernel<<<(unsigned)ntiles, TILE, smem, s>>>(p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(slot.ev[1], s));
+        launches = 2;
+    }
+    CK(cudaMemcpyAsync(slot.h_status, wk, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess)
+        return fail(ctx, REGK_ERR_CUDA, "regk_service_records: kernel execution failed: %s", cudaGetErrorString(e));
+    const DevStatus st = *slot.h_status;
+    res->n = n;
+    res->launches = launches;
+    res->bad_bits = st.bad_bits;
+    res->first_bad = st.bad_bits ? ~st.first_bad : 0;
+    if (n) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, slot.ev[0], slot.ev[1]);
+        res->kernel_ms = res->json_kernel_ms = ms;
+    }
+    if (st.overflow)
+        return fail(ctx, REGK_ERR_CUDA, "internal error: output capacity bound exceeded");
+    if (st.bad_bits)
+        return fail(ctx, REGK_ERR_OUT_OF_DOMAIN,
+            "service record %llu is outside the supported input domain (REGK_BAD bits 0x%x); no output produced",
+            (unsigned long long)res->first_bad, st.bad_bits);
+    res->json_total = st.json_total;
+    ctx->last_path_off = nullptr;                   /* the payload buffers were reused */
+    ctx->last_json_off = nullptr;
+    if (out_dev) {
+        res->flags = REGK_OUT_DEVICE;
+        res->json_bytes = (uint8_t *)ctx->json_bytes.p;
+        res->json_off = (uint64_t *)ctx->json_off.p;
+        return REGK_OK;
+    }
+    if ((rc = ensure_host(ctx, ctx->h_json_bytes, st.json_total + 16)) || (rc = ensure_host(ctx, ctx->h_json_off, (n + 1) * 8)))
+        return rc;
+    if (st.json_total)
+        CK(cudaMemcpyAsync(ctx->h_json_bytes.p, ctx->json_bytes.p, st.json_total, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_json_off.p, ctx->json_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    res->json_bytes = (uint8_t *)ctx->h_json_bytes.p;
+    res->json_off = (uint64_t *)ctx->h_json_off.p;
+    return REGK_OK;
+}
+
+int regk_jute_frames(regk_ctx *ctx, uint32_t flags, int32_t xid_base, uint32_t zk_flags, regk_frames *out)
+{
+    if (!ctx || !out)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_jute_frames: NULL argument");
+    memset(out, 0, sizeof *out);
+    if (ctx->pending)
+        return fail(ctx, REGK_ERR_STATE, "regk_jute_frames: batches are still in flight; finish them first");
+    if (!ctx->last_path_off || !ctx->last_json_off || ctx->last_n != ctx->last_json_n)
+        return fail(ctx, REGK_ERR_STATE, "regk_jute_frames: no finished batch with both a path and a payload stream on this context");
+    const uint64_t n = ctx->last_n;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool dev_out = flags & REGK_OUT_DEVICE;
+    out->n = n;
+    out->flags = dev_out ? REGK_OUT_DEVICE : 0;
+    /* totals of the two streams: the closing offsets on the device */
+    unsigned long long tot[2] = {0, 0};
+    CK(cudaMemcpyAsync(&tot[0], ctx->last_path_off + n, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&tot[1], ctx->last_json_off + n, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t total = tot[0] + tot[1] + (uint64_t)JUTE_FIXED * n;
+    int rc;
+    if ((rc = ensure_dev(ctx, ctx->jute_bytes, total + 32)) || (rc = ensure_dev(ctx, ctx->jute_off, (n + 1) * 8)))
+        return rc;
+    if ((rc = ensure_dev(ctx, ctx->svc_work, 256)))
+        return rc;
+    CK(cudaMemsetAsync(ctx->svc_work.p, 0, sizeof(DevStatus), s));
+    if (n == 0)
+        CK(cudaMemsetAsync(ctx->jute_off.p, 0, 8, s));
+    cudaEvent_t e0 = ctx->slots[0].ev[0], e1 = ctx->slots[0].ev[1];
+    if (n) {
+        JuteParams p{};
+        p.n = n;
+        p.path_bytes = ctx->last_path_bytes;
+        p.path_off = ctx->last_path_off;
+        p.json_bytes = ctx->last_json_bytes;
+        p.json_off = ctx->last_json_off;
+        p.out_bytes = (uint8_t *)ctx->jute_bytes.p;
+        p.out_off = (unsigned long long *)ctx->jute_off.p;
+        p.out_capacity = total;
+        p.xid_base = xid_base;
+        p.zk_flags = zk_flags;
+        p.status = (DevStatus *)ctx->svc_work.p;
+        const uint64_t mean = total / n + 1;
+        p.out_cap = (uint32_t)align16(std::min<uint64_t>(mean * JUTE_TILE * 9 / 8 + 1024, 98304));
+        const size_t smem = (size_t)p.out_cap + 32;
+        static std::mutex mu;
+        static size_t high[64];
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (smem > high[ctx->device & 63]) {
+                CK(cudaFuncSetAttribute(regk_jute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                high[ctx->device & 63] = smem;
+            }
+        }
+        CK(cudaEventRecord(e0, s));
+        regk_jute_kernel<<<(unsigned)((n + JUTE_TILE - 1) / JUTE_TILE), JUTE_THREADS, smem, s>>>(p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, s));
+        out->launches = 1;
+    }
+    CK(cudaMemcpyAsync(ctx->slots[0].h_status, ctx->svc_work.p, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess)
+        return fail(ctx, REGK_ERR_CUDA, "regk_jute_frames: kernel execution failed: %s", cudaGetErrorString(e));
+    if (ctx->slots[0].h_status->overflow)
+        return fail(ctx, REGK_ERR_CUDA, "internal error: frame capacity bound exceeded");
+    if (n)
+        cudaEventElapsedTime(&out->kernel_ms, e0, e1);
+    out->total = total;
+    if (dev_out) {
+        out->frame_bytes = (const uint8_t *)ctx->jute_bytes.p;
+        out->frame_off = (const uint64_t *)ctx->jute_off.p;
+        return REGK_OK;
+    }
+    if ((rc = ensure_host(ctx, ctx->h_jute_bytes, total + 16)) || (rc = ensure_host(ctx, ctx->h_jute_off, (n + 1) * 8)))
+        return rc;
+    if (total)
+        CK(cudaMemcpyAsync(ctx->h_jute_bytes.p, ctx->jute_bytes.p, total, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_jute_off.p, ctx->jute_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    out->frame_bytes = (const uint8_t *)ctx->h_jute_bytes.p;
+    out->frame_off = (const uint64_t *)ctx->h_jute_off.p;
+    return REGK_OK;
+}
+
+int regk_decode(regk_ctx *ctx, const regk_decode_in *in, regk_decode_out *out)
+{
+    if (!ctx || !in || !out)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_decode: NULL argument");
+    static_assert(sizeof(regk_decoded) == sizeof(Decoded), "regk_decoded layout");
+    memset(out, 0, sizeof *out);
+    if (ctx->pending)
+        return fail(ctx, REGK_ERR_STATE, "regk_decode: batches are still in flight; finish them first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool last = in->flags & REGK_DECODE_LAST, in_dev = last || (in->flags & REGK_IN_DEVICE);
+    const bool dev_out = in->flags & REGK_OUT_DEVICE;
+    uint64_t n = in->n, path_total = in->path_total, json_total = in->json_total;
+    const uint8_t *pb = in->path_bytes, *jb = in->json_bytes;
+    const uint64_t *po = in->path_off, *jo = in->json_off;
+    int rc;
+    if (last) {
+        if (!ctx->last_path_off && !ctx->last_json_off)
+            return fail(ctx, REGK_ERR_STATE, "regk_decode: no finished batch on this context");
+        n = ctx->last_path_off ? ctx->last_n : ctx->last_json_n;
+        pb = ctx->last_path_off ? ctx->last_path_bytes : nullptr;
+        po = (const uint64_t *)ctx->last_path_off;
+        jb = ctx->last_json_off ? ctx->last_json_bytes : nullptr;
+        jo = (const uint64_t *)ctx->last_json_off;
+        unsigned long long tot[2] = {0, 0};
+        if (po)
+            CK(cudaMemcpyAsync(&tot[0], po + n, 8, cudaMemcpyDeviceToHost, s));
+        if (jo)
+            CK(cudaMemcpyAsync(&tot[1], jo + n, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        path_total = tot[0];
+        json_total = tot[1];
+    } else {
+        if (n >= (1ull << 32))
+            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_decode: n must be < 2^32 per call");
+        if (n && !po && !jo)
+            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_decode: neither a path nor a payload stream given");
+        if ((po && !pb && n) || (jo && !jb && n))
+            return fail(ctx, REGK_ERR_INVALID_ARG, "regk_decode: offsets without bytes");
+        if (!in_dev) {
+            path_total = (po && n) ? po[n] : 0;
+            json_total = (jo && n) ? jo[n] : 0;
+            /* offsets are used as memory ranges by the kernel: they must be monotone and end at the total */
+            for (uint64_t i = 0; i < n; i++)
+                if ((po && (po[i] > po[i + 1])) || (jo && (jo[i] > jo[i + 1])))
+                    return fail(ctx, REGK_ERR_INVALID_ARG, "regk_decode: offsets are not monotone at record %llu", (unsigned long long)i);
+            const void *src[4] = {pb, po, jb, jo};
+            const size_t sz[4] = {(size_t)path_total, po ? (size_t)(n + 1) * 8 : 0, (size_t)json_total, jo ? (size_t)(n + 1) * 8 : 0};
+            const void *dev[4] = {nullptr, nullptr, nullptr, nullptr};
+            for (int i = 0; i < 4; i++) {
+                if (!src[i] || !n || ((i == 0 || i == 2) && !src[i + 1]))
+                    continue;
+                if ((rc = ensure_dev(ctx, ctx->dec_in[i], sz[i] + 16)))
+                    return rc;
+                if (sz[i])
+                    CK(cudaMemcpyAsync(ctx->dec_in[i].p, src[i], sz[i], cudaMemcpyHostToDevice, s));
+                dev[i] = ctx->dec_in[i].p;
+            }
+            pb = (const uint8_t *)dev[0];
+            po = (const uint64_t *)dev[1];
+            jb = (const uint8_t *)dev[2];
+            jo = (const uint64_t *)dev[3];
+        }
+    }
+    if (!po)
+        pb = nullptr;
+    if (!jo)
+        jb = nullptr;
+    const uint64_t ports_len = json_total / 2 + 1;
+    if ((rc = ensure_dev(ctx, ctx->dec_rec, (n + 1) * sizeof(Decoded))) || (rc = ensure_dev(ctx, ctx->dec_dom, path_total + 16)) ||
+        (rc = ensure_dev(ctx, ctx->dec_ports, ports_len * 4 + 16)))
+        return rc;
+    out->n = n;
+    out->flags = dev_out ? REGK_OUT_DEVICE : 0;
+    out->dom_bytes_len = path_total;
+    out->ports_len = ports_len;
+    cudaEvent_t e0 = ctx->slots[0].ev[0], e1 = ctx->slots[0].ev[1];
+    if (n) {
+        DecodeParams p{};
+        p.n = n;
+        p.path_bytes = po ? (pb ? pb : (const uint8_t *)ctx->dec_dom.p) : nullptr;     /* an empty stream still has offsets */
+        p.path_off = (const unsigned long long *)po;
+        p.json_bytes = jo ? (jb ? jb : (const uint8_t *)ctx->dec_dom.p) : nullptr;
+        p.json_off = (const unsigned long long *)jo;
+        p.host_nodes = in->host_nodes;
+        p.out = (Decoded *)ctx->dec_rec.p;
+        p.dom_bytes = (uint8_t *)ctx->dec_dom.p;
+        p.ports = (uint32_t *)ctx->dec_ports.p;
+        CK(cudaEventRecord(e0, s));
+        regk_decode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e1, s));
+        out->launches = 1;
+    }
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess)
+        return fail(ctx, REGK_ERR_CUDA, "regk_decode: kernel execution failed: %s", cudaGetErrorString(e));
+    if (n)
+        cudaEventElapsedTime(&out->kernel_ms, e0, e1);
+    if (dev_out) {
+        out->rec = (const regk_decoded *)ctx->dec_rec.p;
+        out->dom_bytes = (const uint8_t *)ctx->dec_dom.p;
+        out->ports = (const uint32_t *)ctx->dec_ports.p;
+        return REGK_OK;
+    }
+    if ((rc = ensure_host(ctx, ctx->h_dec_rec, (n + 1) * sizeof(Decoded))) || (rc = ensure_host(ctx, ctx->h_dec_dom, path_total + 16)) ||
+        (rc = ensure_host(ctx, ctx->h_dec_ports, ports_len * 4 + 16)))
+        return rc;
+    if (n) {
+        CK(cudaMemcpyAsync(ctx->h_dec_rec.p, ctx->dec_rec.p, n * sizeof(Decoded), cudaMemcpyDeviceToHost, s));
+        if (po && path_total)
+            CK(cudaMemcpyAsync(ctx->h_dec_dom.p, ctx->dec_dom.p, path_total, cudaMemcpyDeviceToHost, s));
+        if (jo)
+            CK(cudaMemcpyAsync(ctx->h_dec_ports.p, ctx->dec_ports.p, ports_len * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    out->rec = (const regk_decoded *)ctx->h_dec_rec.p;
+    out->dom_bytes = (const uint8_t *)ctx->h_dec_dom.p;
+    out->ports = (const uint32_t *)ctx->h_dec_ports.p;
     return REGK_OK;
 }
 

@@ -21,6 +21,7 @@
 #ifndef REGK_CORE_CUH
 #define REGK_CORE_CUH
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -49,6 +50,8 @@ enum : uint32_t {
     BAD_ADDR_BYTE = 1u << 2,
     BAD_TYPE_ID = 1u << 3,
     BAD_TOO_LARGE = 1u << 4,
+    BAD_SERVICE_BYTE = 1u << 5,
+    BAD_KEY_ORDER = 1u << 6,
 };
 
 /* ---------------------------------------------------------------- SWAR -- */
@@ -1093,6 +1096,80 @@ RG_HD void emit_json(const FSrc &blob, const TypeFrag &tf, const uint32_t (&aw)[
     } else {
         sink.put(RG_LE4('"', '}', '}', 0), 3);
     }
+}
+
+/* ---------------------------------------- service records (regk_service.cuh) -- */
+
+/*
+ * {"type":"service","service":{"type":"service","service":{<srvce, proto, port, ttl in the caller's key order>}}}
+ * - what lib/register.js:58-62 puts at the domain's node (registration.service as asserted at :186-199).
+ */
+/* append a string literal, four bytes per sink operation (indices are compile-time constants) */
+template <class Sink, size_t N>
+RG_HD void put_lit(Sink &sink, const char (&lit)[N])
+{
+    constexpr uint32_t n = (uint32_t)N - 1u;
+    #pragma unroll
+    for (uint32_t i = 0; i + 4u <= n; i += 4u)
+        sink.put4(RG_LE4(lit[i], lit[i + 1], lit[i + 2], lit[i + 3]));
+    constexpr uint32_t r = n & 3u, b = n - r;
+    if (r == 1u)
+        sink.put1((uint8_t)lit[b]);
+    else if (r == 2u)
+        sink.put(RG_LE4(lit[b], lit[b + 1 < n ? b + 1 : b], 0, 0), 2);
+    else if (r == 3u)
+        sink.put(RG_LE4(lit[b], lit[b + 1 < n ? b + 1 : b], lit[b + 2 < n ? b + 2 : b], 0), 3);
+}
+
+/* length-only twin of the sinks for literals and strings */
+struct LenSink {
+    uint32_t n;
+    RG_HD void put(uint32_t, uint32_t k) { n += k; }
+    RG_HD void put4(uint32_t) { n += 4; }
+    RG_HD void put8(uint32_t, uint32_t, uint32_t k) { n += k; }
+    RG_HD void put1(uint32_t) { n += 1; }
+};
+
+/* key ids of key_order: two bits each, first member in bits 0-1 */
+enum : uint32_t { KEY_SRVCE = 0, KEY_PROTO = 1, KEY_PORT = 2, KEY_TTL = 3, KEY_ORDER_DEFAULT = 0xE4 /* 3,2,1,0 from the top */ };
+
+RG_HD bool key_order_ok(uint32_t o)
+{
+    const uint32_t seen = (1u << (o & 3u)) | (1u << ((o >> 2) & 3u)) | (1u << ((o >> 4) & 3u)) | (1u << ((o >> 6) & 3u));
+    return seen == 0xFu;
+}
+
+/* the strings are copied without their bytes being looked at: `len_only` sinks skip the loads altogether */
+template <class Src, class Sink>
+RG_HD void emit_service(const Src &ssrc, uint32_t s0, uint32_t sl, const Src &psrc, uint32_t p0, uint32_t pl,
+    uint32_t port, int32_t ttl, uint32_t order, Sink &sink, bool len_only)
+{
+    put_lit(sink, "{\"type\":\"service\",\"service\":{\"type\":\"service\",\"service\":{");
+    #pragma unroll 1
+    for (uint32_t i = 0; i < 4u; i++) {
+        const uint32_t key = (order >> (2u * i)) & 3u;
+        if (i)
+            sink.put1(',');
+        if (key == KEY_SRVCE || key == KEY_PROTO) {
+            if (key == KEY_SRVCE)
+                put_lit(sink, "\"srvce\":\"");
+            else
+                put_lit(sink, "\"proto\":\"");
+            const uint32_t o = key == KEY_SRVCE ? s0 : p0, l = key == KEY_SRVCE ? sl : pl;
+            if (len_only)
+                sink.put(0u, l);
+            else
+                copy_bytes<false>(key == KEY_SRVCE ? ssrc : psrc, o, l, sink);
+            sink.put1('"');
+        } else if (key == KEY_PORT) {
+            put_lit(sink, "\"port\":");
+            put_u32_dec(port, sink);
+        } else {
+            put_lit(sink, "\"ttl\":");
+            put_i32_dec(ttl, sink);
+        }
+    }
+    put_lit(sink, "}}}");
 }
 
 /* ------------------------------------ setupDirectories (regk_parents.cuh) -- */

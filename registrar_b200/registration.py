@@ -215,13 +215,29 @@ def _node_dirname(p: str) -> str:
 
 
 # ------------------------------------------------------------------------------------ pipeline steps
+class Serialized(bytes):
+    """A znode payload already serialised by the GPU path: the client sends these bytes as they are instead of
+    JSON.stringify-ing an object (zk.create gets the same through its `serialized` option)."""
+
+
+def service_payloads(services: Iterable[dict], ctx: Optional[_native.Context] = None):
+    """N `registration.service` objects -> the payloads of their service records, one GPU call."""
+    from .batch import ServiceBatch
+    return (ctx or _ctx()).service_records(ServiceBatch.from_services(services))
+
+
 def _register_service(opts, cb):
-    # lib/register.js:45-75
+    # lib/register.js:45-75.  The record {type:'service', service: registration.service} is serialised on the
+    # GPU (regk_service_records); members outside srvce/proto/port/ttl are not representable there and raise.
     if not _get(opts["registration"], "service"):
         cb()
         return
     cb = once(cb)
-    obj = {"type": "service", "service": _get(opts["registration"], "service")}
+    try:
+        obj = Serialized(service_payloads([_get(opts["registration"], "service")], _ctx(opts)).json(0))
+    except Exception as e:  # noqa: BLE001
+        cb(e)
+        return
 
     def done(err=None, *_):
         if err:

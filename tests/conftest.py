@@ -42,6 +42,7 @@ def emul(built):
         getattr(lib, f).restype = C.c_uint32
     lib.emul_build_blob.restype = C.c_int
     lib.emul_parents.restype = C.c_uint64
+    lib.emul_services.restype = C.c_uint64
     return lib
 
 

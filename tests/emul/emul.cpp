@@ -340,3 +340,37 @@ extern "C" int emul_build_blob(const char *const *types, const uint32_t *lens, u
     *blob_len = (uint32_t)blob.size();
     return 0;
 }
+
+/* service-record payloads (regk_core.cuh emit_service): every record through the length sink, the byte sink and a
+   word sink at output phase `phase`; returns 0 when the three agree, else 1 + the record index */
+extern "C" uint64_t emul_services(uint64_t n, const uint8_t *srvce_bytes, const uint32_t *srvce_off, const uint8_t *proto_bytes,
+    const uint32_t *proto_off, const uint32_t *port, const int32_t *ttl, const uint8_t *key_order, uint32_t phase,
+    uint8_t *out_bytes, uint64_t *out_off)
+{
+    const GuardedWords ssrc{(const uint32_t *)srvce_bytes}, psrc{(const uint32_t *)proto_bytes};
+    uint64_t base = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        const uint32_t s0 = srvce_off[r], sl = srvce_off[r + 1] - s0, p0 = proto_off[r], pl = proto_off[r + 1] - p0;
+        const uint32_t order = key_order ? key_order[r] : (uint32_t)KEY_ORDER_DEFAULT;
+        if (!key_order_ok(order))
+            return 1 + r;
+        LenSink ls{0};
+        emit_service(ssrc, s0, sl, psrc, p0, pl, port[r], ttl[r], order, ls, true);
+        ByteSink bs;
+        bs.init(out_bytes + base);
+        emit_service(ssrc, s0, sl, psrc, p0, pl, port[r], ttl[r], order, bs, false);
+        if ((uint64_t)(bs.p - (out_bytes + base)) != ls.n)
+            return 1 + r;
+        std::vector<uint32_t> img((phase + ls.n) / 4 + 8, 0);
+        WordSink ws;
+        ws.init(img.data(), phase);
+        emit_service(ssrc, s0, sl, psrc, p0, pl, port[r], ttl[r], order, ws, false);
+        ws.tail();
+        if (memcmp((const uint8_t *)img.data() + phase, out_bytes + base, ls.n) != 0)
+            return 1 + r;
+        out_off[r] = base;
+        base += ls.n;
+    }
+    out_off[n] = base;
+    return 0;
+}

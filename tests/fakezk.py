@@ -51,8 +51,9 @@ class FakeZk:
         self.calls.append(("put", path, obj))
         if self._maybe_fail("put", path, cb):
             return
-        # zkplus serialises objects itself
-        self.nodes[path] = {"data": json.dumps(obj, separators=(",", ":")).encode(), "ephemeral": False}
+        # zkplus serialises objects itself; the GPU path hands over bytes (registration.Serialized)
+        data = bytes(obj) if isinstance(obj, (bytes, bytearray)) else json.dumps(obj, separators=(",", ":")).encode()
+        self.nodes[path] = {"data": data, "ephemeral": False}
         cb(None)
 
     def stat(self, path, cb):

@@ -49,6 +49,10 @@ def test_struct_layouts_match_header(built):
     #include "regk.h"
     int main(void) {
         printf("%zu %zu %zu ", sizeof(regk_parents), offsetof(regk_parents, unique_first), offsetof(regk_parents, kernel_ms));
+        printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu ", sizeof(regk_service_batch), offsetof(regk_service_batch, key_order),
+               sizeof(regk_frames), offsetof(regk_frames, kernel_ms), sizeof(regk_decoded), sizeof(regk_decode_in),
+               offsetof(regk_decode_in, json_off), sizeof(regk_decode_out), offsetof(regk_decode_out, ports),
+               offsetof(regk_decode_out, kernel_ms));
         printf("%zu %zu %zu %zu %zu ", sizeof(regk_job), offsetof(regk_job, mailbox), offsetof(regk_job, timeout_ms),
                offsetof(regk_result, job_path_base), offsetof(regk_result, job_json_total));
         printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(regk_batch), offsetof(regk_batch, domain_bytes),
@@ -62,6 +66,10 @@ def test_struct_layouts_match_header(built):
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
     got = [C.sizeof(_native.CParents), _native.CParents.unique_first.offset, _native.CParents.kernel_ms.offset,
+           C.sizeof(_native.CServiceBatch), _native.CServiceBatch.key_order.offset, C.sizeof(_native.CFrames),
+           _native.CFrames.kernel_ms.offset, _native.DECODED_DTYPE.itemsize, C.sizeof(_native.CDecodeIn),
+           _native.CDecodeIn.json_off.offset, C.sizeof(_native.CDecodeOut), _native.CDecodeOut.ports.offset,
+           _native.CDecodeOut.kernel_ms.offset,
            C.sizeof(_native.CJob), _native.CJob.mailbox.offset, _native.CJob.timeout_ms.offset,
            _native.CResult.job_path_base.offset, _native.CResult.job_json_total.offset,
            C.sizeof(_native.CBatch), _native.CBatch.domain_bytes.offset, _native.CBatch.ports_present.offset,

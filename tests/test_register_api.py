@@ -166,8 +166,10 @@ def test_call_traces_equal_the_executed_reference(built):
             if c[0] == "create":
                 got.append(["create", c[1], c[2].decode(), "+".join(c[3])])
             elif c[0] == "put":
-                import json
-                got.append(["put", c[1], json.dumps(c[2], separators=(",", ":"))])
+                # the service record's bytes come from the GPU (regk_service_records), like create()'s payload
+                from registrar_b200.registration import Serialized
+                assert isinstance(c[2], Serialized)
+                got.append(["put", c[1], c[2].decode()])
             else:
                 got.append([c[0], c[1]])
         got.append(["registered"] + r["znodes"])

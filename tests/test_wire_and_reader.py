@@ -1,0 +1,194 @@
+"""SURVEY.md §8(f).3 ZooKeeper wire framing and §8(f).4 the reader side.
+
+Framing: parity is UNPINNED (zkplus / ZooKeeper are not in the reference tree, package.json:20) - the kernel is
+compared with an independent Python restatement of the published zookeeper.jute layout, and the restatement itself
+with a hand-assembled frame.  Reader: decode(encode(x)) == x on the synthetic configurations, plus what the README
+(:587-664) says a valid record looks like."""
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import oracle, pyoracle
+from registrar_b200 import synth
+from registrar_b200.batch import RecordBatch, ServiceBatch
+
+
+def test_jute_restatement_against_a_hand_assembled_frame():
+    path, data = b"/us/joyent/test/h", b'{"type":"host"}'
+    f = pyoracle.jute_create_request(path, data, xid=7, flags=1)
+    want = (b"\x00\x00\x00" + bytes([len(path) + len(data) + 47]) + b"\x00\x00\x00\x07" + b"\x00\x00\x00\x01" +
+            b"\x00\x00\x00\x11" + path + b"\x00\x00\x00\x0f" + data + b"\x00\x00\x00\x01" + b"\x00\x00\x00\x1f" +
+            b"\x00\x00\x00\x05world" + b"\x00\x00\x00\x06anyone" + b"\x00\x00\x00\x01")
+    assert f == want and len(f) == len(path) + len(data) + 51
+    assert struct.unpack(">i", f[:4])[0] == len(f) - 4
+
+
+def test_path_to_domain_restatement():
+    assert pyoracle.path_to_domain("/us/joyent/emy-10/authcache/a2674d3b-a9c4-46bc-a835-b6ce21d522c2", True) == \
+        ("authcache.emy-10.joyent.us", "a2674d3b-a9c4-46bc-a835-b6ce21d522c2")     # README.md:474-477
+    assert pyoracle.path_to_domain("/com/joyent/us-east/moray/1", False) == ("1.moray.us-east.joyent.com", None)
+    for d in ("a..b", "a.", ".a", "", "x", "a.b.c"):
+        assert pyoracle.path_to_domain(pyoracle.domain_to_path(d), False)[0] == d.lower()
+    assert pyoracle.path_to_domain("/h", True) == ("", "h")
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.fixture(scope="module")
+def ctx(built):
+    from registrar_b200 import _native
+    c = _native.Context(0)
+    yield c
+    c.close()
+
+
+def frames_of(res, xid_base, flags):
+    return b"".join(pyoracle.jute_create_request(res.path(i), res.json(i), xid_base + i, flags) for i in range(res.n))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,n", [("config1", 1000), ("config3", 20011), ("config5", 5000)])
+def test_gpu_jute_frames(ctx, cfg, n):
+    batch = synth.generate(cfg, n=n)
+    res = ctx.register_batch(batch)
+    fb, fo, ms = ctx.jute_frames(xid_base=1000, zk_flags=1)
+    want = frames_of(res, 1000, 1)
+    assert int(fo[-1]) == len(want) == res.path_total + res.json_total + 51 * n
+    assert np.array_equal(fo[:-1], res.path_off[:-1] + res.json_off[:-1] + np.uint64(51) * np.arange(n, dtype=np.uint64))
+    assert bytes(fb) == want
+    # every frame parses back: length prefix, xid, opcode, path, data
+    for i in (0, n // 2, n - 1):
+        f = bytes(fb[int(fo[i]):int(fo[i + 1])])
+        ln, xid, op, pl = struct.unpack(">iiii", f[:16])
+        assert ln == len(f) - 4 and xid == 1000 + i and op == 1 and f[16:16 + pl] == res.path(i)
+
+
+@pytest.mark.gpu
+def test_gpu_jute_frames_edges(ctx):
+    from registrar_b200._native import RegkError
+    recs = [{"domain": "a.b", "hostname": "h", "type": "host", "address": "1.2.3.4"}]
+    for n in (1, 63, 64, 65, 129):
+        res = ctx.register_batch(RecordBatch.from_records(recs * n))
+        fb, fo, _ = ctx.jute_frames(xid_base=-5, zk_flags=0)          # persistent nodes, negative xid
+        assert bytes(fb) == frames_of(res, -5, 0)
+    # the global-memory path: an image budget too small for any tile
+    batch = synth.generate("config5", n=3000)
+    res = ctx.register_batch(batch)
+    fb, fo, _ = ctx.jute_frames(2, 1)
+    assert bytes(fb) == frames_of(res, 2, 1)
+    ctx.register_batch(RecordBatch.from_records(recs), payloads=False)
+    with pytest.raises(RegkError):
+        ctx.jute_frames()                                            # needs both streams
+
+
+def slot(dom_bytes, off, i, ln):
+    a = int(off[i])
+    return bytes(dom_bytes[a:a + int(ln)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,n", [("config1", 1000), ("config3", 30011), ("config5", 8000)])
+def test_gpu_round_trip_decode_of_encode(ctx, cfg, n):
+    from registrar_b200 import _native as nv
+    batch = synth.generate(cfg, n=n)
+    res = ctx.register_batch(batch)
+    rec, dom, ports, ms = ctx.decode(last=True, host_nodes=True)
+    assert len(rec) == n and np.all(rec["flags"] == (nv.DEC_PATH_OK | nv.DEC_HOST_RECORD))
+    L = np.diff(batch.domain_off.astype(np.int64))
+    assert np.array_equal(rec["dom_len"], L) and np.all(rec["host_len"] == 36)
+    want_ttl = batch.ttl.astype(np.int64)
+    assert np.array_equal(rec["ttl"].astype(np.int64), want_ttl)
+    k = np.diff(batch.ports_off.astype(np.int64))
+    assert np.array_equal(np.where(rec["nports"] == 0xFFFFFFFF, 0, rec["nports"]), k)
+    for i in list(range(0, n, 97)) + [n - 1]:
+        r = batch.record(i)
+        assert slot(dom, res.path_off, i, rec["dom_len"][i]) == r["domain"].lower()
+        p, j = res.path(i), res.json(i)
+        assert p[rec["host_pos"][i]:rec["host_pos"][i] + rec["host_len"][i]] == r["hostname"]
+        assert j[rec["type_pos"][i]:rec["type_pos"][i] + rec["type_len"][i]] == r["type"]
+        assert j[rec["addr_pos"][i]:rec["addr_pos"][i] + rec["addr_len"][i]] == r["address"]
+        a = int(res.json_off[i]) >> 1
+        assert list(ports[a:a + (0 if r["ports"] is None else len(r["ports"]))]) == (r["ports"] or [])
+    # the same through explicit host streams, and the alias view of the same domains
+    rec2, dom2, ports2, _ = ctx.decode(res.path_bytes, res.path_off, res.json_bytes, res.json_off, host_nodes=True)
+    assert np.array_equal(rec, rec2) and np.array_equal(dom[:len(dom2)], dom2)
+    ab = RecordBatch.from_records([batch.record(i) for i in range(0, n, 53)], alias=True)
+    ares = ctx.register_batch(ab, payloads=False)
+    arec, adom, _, _ = ctx.decode(ares.path_bytes, ares.path_off, host_nodes=False)
+    for i in range(ab.n):
+        assert slot(adom, ares.path_off, i, arec["dom_len"][i]) == ab.record(i)["domain"].lower()
+
+
+def streams(items):
+    off = np.zeros(len(items) + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in items])
+    return np.frombuffer(b"".join(items), np.uint8).copy() if items else np.zeros(0, np.uint8), off
+
+
+@pytest.mark.gpu
+def test_gpu_decode_edge_cases_and_the_readme_rules(ctx):
+    from registrar_b200 import _native as nv
+    # un-normalised alias paths invert exactly (reference domainToPath keeps empty labels)
+    doms = ["a..b", "a.", ".a", "", "x", "1.moray.us-east.joyent.com", "..", "a.b.c.d.e.f.g"]
+    pb, po = streams([pyoracle.domain_to_path(d).encode() for d in doms])
+    rec, dom, _, _ = ctx.decode(pb, po, host_nodes=False)
+    assert [slot(dom, po, i, rec["dom_len"][i]).decode() for i in range(len(doms))] == doms
+    assert np.all(rec["flags"] == nv.DEC_PATH_OK)
+    # host nodes, including the root domain and broken paths
+    paths = [b"/us/joyent/h1", b"/h", b"no-slash", b"/us/joyent/", b"/"]
+    pb, po = streams(paths)
+    rec, dom, _, _ = ctx.decode(pb, po, host_nodes=True)
+    assert [int(f) for f in rec["flags"]] == [nv.DEC_PATH_OK, nv.DEC_PATH_OK, nv.DEC_BAD_PATH, nv.DEC_BAD_PATH, nv.DEC_BAD_PATH]
+    assert slot(dom, po, 0, rec["dom_len"][0]) == b"joyent.us" and rec["dom_len"][1] == 0
+    assert paths[0][rec["host_pos"][0]:] == b"h1" and paths[1][rec["host_pos"][1]:] == b"h"
+    # payloads: README.md:623-630 (compact), :539-547, test/register.test.js:123-129, service records, and what is refused
+    good = [b'{"type":"load_balancer","address":"172.27.10.72","load_balancer":{"address":"172.27.10.72","ports":[80]}}',
+            b'{"type":"redis_host","address":"172.27.10.62","ttl":30,"redis_host":{"address":"172.27.10.62","ports":[6379]}}',
+            b'{"type":"host","address":"127.0.0.1","host":{"address":"127.0.0.1"}}',
+            b'{"type":"host","address":"127.0.0.1","ttl":-5,"host":{"address":"127.0.0.1","ports":[]}}',
+            b'{"type":"quote\\"d","address":"1.1.1.1","quote\\"d":{"address":"1.1.1.1","ports":[0,4294967295]}}']
+    svc = [b'{"type":"service","service":{"type":"service","service":{"srvce":"_http","proto":"_tcp","port":80,"ttl":60}}}',
+           b'{"type":"service","service":{"type":"service","service":{"ttl":15,"port":8080,"proto":"_tcp","srvce":"_http"}}}']
+    bad = [(b'{"type":"host","address":"1.1.1.1","moray_host":{"address":"1.1.1.1"}}', nv.DEC_HOST_RECORD | nv.DEC_KEY_MISMATCH),
+           (b'{"type":"host","address":"1.1.1.1","host":{"address":"1.1.1.2"}}', nv.DEC_HOST_RECORD | nv.DEC_ADDR_MISMATCH),
+           (b'{"type":"host","address":"1.1.1.1","ttl":1.5,"host":{"address":"1.1.1.1"}}', nv.DEC_BAD_NUMBER),
+           (b'{"type":"host","address":"1.1.1.1","host":{"address":"1.1.1.1","ports":[80,"x"]}}', nv.DEC_BAD_NUMBER),
+           (b'{"type":"host","address":"1.1.1.1","host":{"address":"1.1.1.1","ports":[080]}}', nv.DEC_BAD_NUMBER),
+           (b'{"type": "host","address":"1.1.1.1","host":{"address":"1.1.1.1"}}', nv.DEC_NOT_CANONICAL),
+           (b'{"address":"1.1.1.1","type":"host","host":{"address":"1.1.1.1"}}', nv.DEC_NOT_CANONICAL),
+           (b'{"type":"host","address":"1.1.1.1","host":{"address":"1.1.1.1"}}x', nv.DEC_NOT_CANONICAL),
+           (b'{"type":"host","address":"1.1.1.1","host":{"address":"1.1.1.1"}', nv.DEC_NOT_CANONICAL),
+           (b'{"type":"service","service":{"type":"service","service":{"srvce":"_http","proto":"_tcp","ttl":60}}}', nv.DEC_NOT_CANONICAL),
+           (b'', nv.DEC_NOT_CANONICAL), (b'{', nv.DEC_NOT_CANONICAL)]
+    items = good + svc + [b for b, _ in bad]
+    jb, jo = streams(items)
+    rec, _, ports, _ = ctx.decode(json_bytes=jb, json_off=jo)
+    for i, item in enumerate(items):
+        want = nv.DEC_HOST_RECORD if i < len(good) else nv.DEC_SERVICE_RECORD if i < len(good) + len(svc) else bad[i - len(good) - len(svc)][1]
+        assert int(rec["flags"][i]) == want, (item, int(rec["flags"][i]))
+        if want in (nv.DEC_HOST_RECORD, nv.DEC_SERVICE_RECORD):
+            d = pyoracle.decode_payload(item)
+            tp, tl, ap, al = (int(rec[k][i]) for k in ("type_pos", "type_len", "addr_pos", "addr_len"))
+            assert item[ap:ap + al].decode() == d["address"]
+            if i != 4:                                          # escapes are reported raw, not decoded
+                assert item[tp:tp + tl].decode() == d["type"]
+            assert (None if rec["ttl"][i] == -2 ** 31 else int(rec["ttl"][i])) == d["ttl"]
+            a = int(jo[i]) >> 1
+            got = None if rec["nports"][i] == 0xFFFFFFFF else [int(x) for x in ports[a:a + int(rec["nports"][i])]]
+            assert got == d["ports"]
+
+
+@pytest.mark.gpu
+def test_gpu_service_records_decode_back(ctx):
+    from registrar_b200 import _native as nv
+    from test_service_records import random_services
+    rng = np.random.default_rng(3)
+    services = random_services(rng, 2000)
+    sb = ServiceBatch.from_services(services)
+    res = ctx.service_records(sb)
+    rec, _, ports, _ = ctx.decode(json_bytes=res.json_bytes, json_off=res.json_off)
+    assert np.all(rec["flags"] == nv.DEC_SERVICE_RECORD)
+    assert np.array_equal(rec["ttl"], sb.ttl)
+    assert np.array_equal(ports[(res.json_off[:-1] >> np.uint64(1)).astype(np.int64)], sb.port)
+    assert np.array_equal(rec["type_len"], np.diff(sb.srvce_off.astype(np.int64)))
+    assert np.array_equal(rec["addr_len"], np.diff(sb.proto_off.astype(np.int64)))

@@ -11,9 +11,18 @@ def main():
     if os.environ.get('REGK_DOMCAP'):
         ctx.set_option('dom_cap', int(os.environ['REGK_DOMCAP']))
     out = []
+    if not os.environ.get('QUICK_NOCHECK'):      # A/B builds: parity first, on a batch with every shape
+        from oracle import oracle
+        import numpy as np
+        for cfg in ("config3", "config5"):
+            b = synth.generate(cfg, n=30011)
+            got, want = ctx.register_batch(b), oracle.register_batch(b)
+            ok = (np.array_equal(got.path_bytes, want.path_bytes) and np.array_equal(got.json_bytes, want.json_bytes)
+                  and np.array_equal(got.path_off, want.path_off) and np.array_equal(got.json_off, want.json_off))
+            print(json.dumps({"parity": cfg, "ok": bool(ok)}), flush=True)
     for cfg, n in [("config2", 1_000_000), ("config3", 2_000_000), ("config5", 2_000_000)]:
         b = synth.generate(cfg, n=n)
-        for generic in (0, 1):
+        for generic in ((0, 1) if os.environ.get('QUICK_GENERIC') else (0,)):
             ctx.set_option("force_generic", generic)
             ms = []
             for it in range(6):
