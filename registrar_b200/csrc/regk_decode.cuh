@@ -108,6 +108,8 @@ struct Cur {
             if (++digits > 11)
                 return false;
         }
+        if (i < n && (p[i] == '.' || p[i] == 'e' || p[i] == 'E'))
+            return false;                                           /* a JSON number, but not an integer */
         a = neg ? -a : a;
         if (a < lo || a > hi || (neg && a == 0))
             return false;
