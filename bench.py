@@ -348,7 +348,7 @@ def timed_resident_loop(rig, submit, steps, warmup, depth=24):
     """warm-up, then `steps` submissions between two events on the launching stream; returns (ms_total, stats)."""
     torch, ctx = rig.torch, rig.ctx
     inflight = []
-    stats = {"path_ms": 0.0, "json_ms": 0.0, "steps": 0, "launches": 0, "last": None}
+    stats = {"path_ms": 0.0, "json_ms": 0.0, "steps": 0, "launches": 0, "last": None, "generic_tiles": 0}
 
     def drain(limit, count):
         while len(inflight) > limit:
@@ -359,6 +359,7 @@ def timed_resident_loop(rig, submit, steps, warmup, depth=24):
                     stats["json_ms"] += r.json_kernel_ms
                     stats["steps"] += 1
                 stats["launches"] += r.launches
+                stats["generic_tiles"] = max(stats["generic_tiles"], int(r.generic_tiles))
             stats["last"] = r
 
     for i in range(warmup):
@@ -467,6 +468,8 @@ def measure_single(rig, cfg, n, start, steps, warmup, e2e_steps, time_every, ver
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "api": "registrar_b200.Context.submit/collect -> regk_register_batch (host buffers)"},
         "gpu_launches": stats["launches"], "verified": verified,
+        "generic_tiles": {"per_step": stats["generic_tiles"], "of": 2 * ((n + 127) // 128),
+                          "what": "tiles (128 records, both kernels) that outgrew the shared-memory budget and were composed in global memory"},
         "l2": "rotating %d distinct resident batches (%.0f MB of traffic per step, > 126 MB L2)" % (NB, (pbytes + jbytes) / 1e6),
         "_host_batch": host_batches[0],
     }
@@ -603,7 +606,7 @@ def run_b200(args):
                        "compose kernels (tiles pushed to every rank over NVLink), inside `value`"},
         }
         for k in ("roofline", "roofline_kernels", "roofline_both_kernels", "roofline_step", "roofline_nvlink",
-                  "no_collective", "e2e", "gpu_launches", "verified"):
+                  "no_collective", "e2e", "gpu_launches", "verified", "generic_tiles"):
             if k in m:
                 line[k] = m[k]
         if extras:

@@ -136,6 +136,9 @@ typedef struct regk_result {
        entries); path_total / json_total stay the shard's own byte counts. */
     uint64_t        job_path_base, job_path_total;
     uint64_t        job_json_base, job_json_total;
+    uint32_t        generic_tiles;  /* tiles (128 records, counted per kernel) that did not fit the kernels' shared-memory
+                                       budget and were composed straight from / to global memory (about 10x slower) */
+    uint32_t        reserved;
 } regk_result;
 
 /* ---- lifecycle ----------------------------------------------------------- */

@@ -59,7 +59,8 @@ class CResult(C.Structure):          # regk_result
                 ("kernel_ms", C.c_float), ("path_kernel_ms", C.c_float), ("json_kernel_ms", C.c_float),
                 ("json_len_kernel_ms", C.c_float), ("launches", C.c_uint32), ("opaque", C.c_void_p),
                 ("job_path_base", C.c_uint64), ("job_path_total", C.c_uint64),
-                ("job_json_base", C.c_uint64), ("job_json_total", C.c_uint64)]
+                ("job_json_base", C.c_uint64), ("job_json_total", C.c_uint64),
+                ("generic_tiles", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 MAX_PEERS = 16
@@ -210,7 +211,8 @@ class HostResult:
     unless copy=False)."""
 
     def __init__(self, n, path_bytes, path_off, json_bytes, json_off, kernel_ms, path_ms, json_ms, launches,
-                 json_len_ms=0.0):
+                 json_len_ms=0.0, generic_tiles=0):
+        self.generic_tiles = generic_tiles
         self.n = n
         self.path_bytes, self.path_off = path_bytes, path_off
         self.json_bytes, self.json_off = json_bytes, json_off
@@ -323,7 +325,7 @@ class Context:
             n, cp(_as_np(res.path_bytes, int(res.path_total), np.uint8)), cp(_as_np(res.path_off, n + 1, np.uint64)),
             cp(_as_np(res.json_bytes, int(res.json_total), np.uint8)), cp(_as_np(res.json_off, n + 1, np.uint64)),
             float(res.kernel_ms), float(res.path_kernel_ms), float(res.json_kernel_ms), int(res.launches),
-            float(res.json_len_kernel_ms))
+            float(res.json_len_kernel_ms), int(res.generic_tiles))
         self._lib.regk_release(self._h, C.byref(res))
         return out
 
@@ -411,7 +413,7 @@ class Context:
             n, cp(_as_np(res.path_bytes, int(res.path_total), np.uint8)), cp(_as_np(res.path_off, n + 1, np.uint64)),
             cp(_as_np(res.json_bytes, int(res.json_total), np.uint8)), cp(_as_np(res.json_off, n + 1, np.uint64)),
             float(res.kernel_ms), float(res.path_kernel_ms), float(res.json_kernel_ms), int(res.launches),
-            float(res.json_len_kernel_ms))
+            float(res.json_len_kernel_ms), int(res.generic_tiles))
         self._lib.regk_release(self._h, C.byref(res))
         return out
 

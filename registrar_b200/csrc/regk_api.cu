@@ -1161,14 +1161,14 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         pp.host_limit = host_len;
         pp.force_generic = force_generic;
         /* shared-memory budget: 1.25x the mean tile, clamped; tiles that do not fit go generic */
-        const uint64_t mean_dom_tile = dom_len / std::max<uint64_t>(ntiles, 1) + 1;
+        const uint64_t mean_dom_tile = std::min<uint64_t>(dom_len, dom_len * TILE / std::max<uint64_t>(n, 1)) + 1;  /* a FULL tile's share */
         uint32_t dom_cap = (uint32_t)opt_get(ctx, "dom_cap", 0);
         if (!dom_cap)
             dom_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(align16(mean_dom_tile * 5 / 4 + 384), 2048), 49152);
         dom_cap = (uint32_t)((dom_cap + 127) & ~127u);         /* bitmap region stays 16-byte aligned */
         uint32_t host_cap = 0;
         if (!alias) {
-            const uint64_t mean_host_tile = pp.host_off ? host_len / std::max<uint64_t>(ntiles, 1) + 1
+            const uint64_t mean_host_tile = pp.host_off ? std::min<uint64_t>(host_len, host_len * TILE / std::max<uint64_t>(n, 1)) + 1
                                                         : (uint64_t)TILE * b->host_stride;
             host_cap = (uint32_t)std::min<uint64_t>(align16((pp.host_off ? mean_host_tile * 3 / 2 + 512 : mean_host_tile) + 16), 49152);
         }
@@ -1472,6 +1472,7 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     res->first_bad = st.bad_bits ? ~st.first_bad : 0;
     res->path_total = st.path_total;
     res->json_total = st.json_total;
+    res->generic_tiles = st.generic_tiles;
     if (st.overflow)
         return fail(ctx, REGK_ERR_CUDA, "internal error: output capacity bound exceeded");
     if (st.bad_bits) {

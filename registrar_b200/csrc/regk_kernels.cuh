@@ -62,7 +62,7 @@ struct DevStatus {
     unsigned long long path_total;
     unsigned long long json_total;
     uint32_t needs_exact;                       /* a record had empty labels: closed-form path offsets do not hold */
-    uint32_t pad;
+    uint32_t generic_tiles;                     /* tiles (of either kernel) whose bytes did not fit the shared-memory budget */
 };
 
 __device__ __forceinline__ uint4 ldg_nc_v4(const void *p)
@@ -748,6 +748,8 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_PATH) regk_path_kernel(const P
         }
     } else {
         /* generic path: compose straight from / to global memory */
+        if (t == 0)
+            atomicAdd(&p.status->generic_tiles, 1u);
         const unsigned long long HB0 = s_plan.HB0;
         const GuardedWords dsrc{reinterpret_cast<const uint32_t *>(p.domain_bytes)};
         const GuardedWords hsrc{reinterpret_cast<const uint32_t *>(p.host_bytes + (var_host ? 0 : HB0))};
@@ -936,6 +938,8 @@ __global__ void __launch_bounds__(TILE, REGK_MINB_JSON) regk_json_kernel(const J
         else
             flush_out(p.out_bytes, s_out, tile_base, tile_total);
     } else {
+        if (t == 0)
+            atomicAdd(&p.status->generic_tiles, 1u);
         if (live) {
             ByteSink sink;
             sink.init(p.out_bytes + tile_base + local);

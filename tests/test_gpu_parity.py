@@ -42,7 +42,15 @@ def test_synthetic(ctx, config, n, generic):
     ctx.set_option("force_generic", generic)
     try:
         batch = synth.generate(config, n=n)
-        assert_same(ctx.register_batch(batch), oracle.register_batch(batch))
+        got = ctx.register_batch(batch)
+        assert_same(got, oracle.register_batch(batch))
+        ntiles = (n + 127) // 128
+        if generic:
+            assert got.generic_tiles == 2 * ntiles          # every tile of both kernels took the global-memory path
+        elif config != "config5":
+            assert got.generic_tiles == 0
+        else:
+            assert got.generic_tiles <= max(2, ntiles // 50)   # Zipf label lengths: a few tiles may outgrow the budget
     finally:
         ctx.set_option("force_generic", 0)
 
