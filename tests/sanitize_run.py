@@ -37,4 +37,20 @@ b = synth.generate("config3", n=5000, start=3)
 got = ctx.register_batch(b); plen, firsts, ms = ctx.parent_dirs()
 wl, wf = oracle.parent_dirs(oracle.register_batch(b))
 assert np.array_equal(plen, wl) and np.array_equal(firsts, wf)
+# round 2: service records, wire frames, the reader side - every new kernel path once, each against its oracle
+from oracle import pyoracle
+from registrar_b200.batch import ServiceBatch
+svcs = [{"type": "service", "service": dict([("srvce", "_svc%d" % i), ("proto", ["_tcp", "_udp"][i % 2]), ("port", 1 + 977 * i)] +
+                                            ([("ttl", 30 + i)] if i % 3 else []))} for i in range(700)]
+sb = ServiceBatch.from_services(svcs)
+got = ctx.service_records(sb); wb, wo = oracle.service_batch(sb)
+assert np.array_equal(got.json_bytes, wb) and np.array_equal(got.json_off, wo)
+b = synth.generate("config5", n=2100, start=11)
+res = ctx.register_batch(b)
+fb, fo, _ = ctx.jute_frames(xid_base=9, zk_flags=1)
+assert bytes(fb) == b"".join(pyoracle.jute_create_request(res.path(i), res.json(i), 9 + i, 1) for i in range(b.n))
+rec, dom, ports, _ = ctx.decode(last=True, host_nodes=True)
+assert np.all(rec["flags"] == 3) and np.array_equal(rec["dom_len"], np.diff(b.domain_off.astype(np.int64)))
+rec2, _, _, _ = ctx.decode(res.path_bytes, res.path_off, res.json_bytes, res.json_off, host_nodes=True)
+assert np.array_equal(rec, rec2)
 print("sanitize_run ok")
