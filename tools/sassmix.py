@@ -2,7 +2,7 @@ import collections, csv, subprocess, sys, io, re
 rep=sys.argv[1]; kern=sys.argv[2]
 out = subprocess.run(["ncu","-i",rep,"--page","source","--csv","--print-source","sass"],stdout=subprocess.PIPE,stderr=subprocess.DEVNULL).stdout.decode()
 rows=list(csv.reader(io.StringIO(out)))
-hdr=None; cur=None; ops=collections.Counter(); tot=0; lines=[]
+hdr=None; cur=None; ops=collections.Counter(); tot=0; lines=[]; seen=set()
 for r in rows:
     if r and r[0]=='Kernel Name': cur=r[1]
     elif r and r[0]=='Address': hdr=r
@@ -10,6 +10,8 @@ for r in rows:
         try: inst=int(r[hdr.index('Instructions Executed')])
         except: continue
         sass=r[1]
+        if (cur, r[0]) in seen: continue        # the page can list a kernel's SASS more than once
+        seen.add((cur, r[0]))
         m=re.match(r'\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)', sass)
         op=m.group(2) if m else sass[:10]
         ops[op]+=inst; tot+=inst; lines.append((inst,sass.strip()))
