@@ -89,6 +89,21 @@ good = refused == (rank == 1)
 say("JOB", "empty-label", "OK" if good else "MISMATCH")
 ok3 = ok3 and good
 job2.close()
+# a job smaller than the world: a rank with zero records still takes part in the exchanges
+for tiny in (1, 3):
+    tlo, thi = multigpu.shard_range(tiny, rank, world)
+    tshard = synth.generate("config3", n=thi - tlo, start=tlo)
+    twhole = oracle.register_batch(synth.generate("config3", n=tiny, start=0))
+    tcb, tkeep = multigpu.device_batch(tshard, dev)
+    job3 = multigpu.PeerJob(ctx, thi - tlo, 4096, 4096, dev)
+    r5 = job3.wait(job3.step(tcb))
+    g5 = job3.result(r5)
+    good = (np.array_equal(g5.path_bytes.cpu().numpy(), twhole.path_bytes) and np.array_equal(g5.json_bytes.cpu().numpy(), twhole.json_bytes)
+            and np.array_equal(g5.path_off.cpu().numpy().astype(np.uint64), twhole.path_off)
+            and np.array_equal(g5.json_off.cpu().numpy().astype(np.uint64), twhole.json_off))
+    say("JOB", "tiny%d" % tiny, "OK" if good else "MISMATCH")
+    ok3 = ok3 and good
+    job3.close()
 job.close()
 ok = ok and ok3
 say("ALL", "OK" if ok else "MISMATCH")

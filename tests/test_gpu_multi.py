@@ -24,5 +24,5 @@ def test_two_rank_gather_equals_single_stream(built, tmp_path):
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-8000:]
     assert out.stdout.count("PEER OK") == 2, out.stdout[-2000:]
     assert out.stdout.count("ALL OK") == 2, out.stdout[-2000:]
-    for variant in ("shared", "shared-again", "generic", "tiny-tiles", "async", "empty-label"):
+    for variant in ("shared", "shared-again", "generic", "tiny-tiles", "async", "empty-label", "tiny1", "tiny3"):
         assert out.stdout.count("JOB %s OK" % variant) == 2, out.stdout[-3000:]
