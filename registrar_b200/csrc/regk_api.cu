@@ -81,6 +81,10 @@ struct regk_ctx {
                                                    2 = a peer exchange of a job step timed out */
     /* multi-GPU job (regk_job_bind): description, exchange sequence number, per-slot bases {path base, path all,
        rec base, n all, payload base, payload all, -, -} on the device and their pinned host copies */
+    double json_mean_seen = 0.0;                /* payload bytes per record of the batch finished last (same type table) ... */
+    uint64_t json_est_seen = 0;                 /* ... and the a-priori estimate that batch had: the figure is reused only for
+                                                   batches with the same estimate */
+    bool json_learning = true;
     regk_job job{};
     bool job_bound = false;
     unsigned long long job_seq = 0;
@@ -139,6 +143,8 @@ struct regk_ctx {
         uint32_t host_stride = 0;
         bool alias = false;
         bool job = false;                       /* a REGK_JOB_STEP batch */
+        uint64_t json_est = 0;                  /* a-priori payload bytes per record of this batch */
+        bool json_learned = false;              /* its image budget came from json_mean_seen */
         bool in_use = false;
         uint64_t n = 0;
         uint32_t flags = 0;
@@ -718,6 +724,8 @@ int regk_set_types(regk_ctx *ctx, const char *const *types, const uint32_t *lens
     ctx->types = raw;
     ctx->blob_host = blob;
     ctx->max_type_q = maxq;
+    ctx->json_mean_seen = 0.0;
+    ctx->json_learning = true;
     return REGK_OK;
 }
 
@@ -1218,10 +1226,27 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
         jp.force_generic = force_generic;
         uint32_t out_cap = (uint32_t)opt_get(ctx, "json_out_cap", 0);
         if (!out_cap) {
-            /* mean payload estimate: fixed keys + type twice + address twice + ttl + ports */
-            const uint64_t mean = 42 + 2ull * ctx->max_type_q + (n ? 2 * addr_len / n : 0) + 11 +
+            /* mean payload estimate: fixed keys + type twice + address twice + ttl + ports - an upper estimate (the
+               longest type name, six bytes per port).  Once a batch with this type table has been finished the measured
+               bytes per record take over (records of one deployment look alike from batch to batch): config 3's image
+               shrinks from 19.2 to 16.5 KB and two more CTAs fit an SM (payload kernel -4 %).  A budget that turns
+               out too small only sends tiles down the global-memory path (counted in generic_tiles), never wrong. */
+            uint64_t mean = 42 + 2ull * ctx->max_type_q + (n ? 2 * addr_len / n : 0) + 11 +
                 (ports_len ? 11 + (n ? 6 * ports_len / n : 0) : 0) + 2;
-            out_cap = (uint32_t)std::min<uint64_t>(align16(mean * TILE * 9 / 8 + 512), 98304);
+            uint64_t tile_bytes = mean * TILE * 9 / 8 + 512;
+            slot.json_est = mean;
+            slot.json_learned = false;
+            /* only for a batch that LOOKS like the one the figure was measured on (same a-priori estimate, i.e. the
+               same address and port bytes per record); a learned budget that ever produced generic tiles is dropped
+               for good (regk_finish) */
+            if (ctx->json_mean_seen > 0.0 && n >= 4096 && ctx->json_est_seen == mean) {
+                const uint64_t seen = (uint64_t)(ctx->json_mean_seen + 1.0);
+                if (seen < mean) {
+                    tile_bytes = seen * TILE * 17 / 16 + 1024;      /* +6 % and 1 KB: > 4.5 sigma of a 128-record sum */
+                    slot.json_learned = true;
+                }
+            }
+            out_cap = (uint32_t)std::min<uint64_t>(align16(tile_bytes), 98304);
         }
         out_cap = (uint32_t)align16(out_cap);
         jp.out_cap = out_cap;
@@ -1473,6 +1498,13 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
     res->path_total = st.path_total;
     res->json_total = st.json_total;
     res->generic_tiles = st.generic_tiles;
+    if (slot->json_learned && st.generic_tiles) {
+        ctx->json_learning = false;             /* the measured mean misjudged this workload once: never again */
+        ctx->json_mean_seen = 0.0;
+    } else if (ctx->json_learning && !st.bad_bits && !st.overflow && n >= 4096 && st.json_total && slot->json_est) {
+        ctx->json_mean_seen = (double)st.json_total / (double)n;
+        ctx->json_est_seen = slot->json_est;
+    }
     if (st.overflow)
         return fail(ctx, REGK_ERR_CUDA, "internal error: output capacity bound exceeded");
     if (st.bad_bits) {

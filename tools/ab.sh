@@ -7,6 +7,6 @@ for l in sys.stdin:
     try: d=json.loads(l)
     except Exception: print(l.rstrip()); continue
     if 'parity' in d: print('parity', d['parity'], d['ok'])
-    elif d['generic']==0: print(d['config'], 'path', round(d['path_ms']*1000,1), 'json', round(d['json_ms']*1000,1), 'GB/s', round(d['gbps']))
+    elif d['generic']==0: print(d['config'], 'path', round(d['path_ms']*1000,1), 'json', round(d['json_ms']*1000,1), 'GB/s', round(d['gbps']), 'generic_tiles', d.get('generic_tiles'))
 "
 done
