@@ -1745,9 +1745,14 @@ int regk_jute_frames(regk_ctx *ctx, uint32_t flags, int32_t xid_base, uint32_t z
         p.xid_base = xid_base;
         p.zk_flags = zk_flags;
         p.status = (DevStatus *)ctx->svc_work.p;
-        const uint64_t mean = total / n + 1;
-        p.out_cap = (uint32_t)align16(std::min<uint64_t>(mean * JUTE_TILE * 9 / 8 + 1024, 98304));
-        const size_t smem = (size_t)p.out_cap + 32;
+        /* staging budgets: 9/8 of a tile's mean share of each stream plus slack (tiles beyond it go byte-wise) */
+        p.path_cap = (uint32_t)align16(std::min<uint64_t>(tot[0] * JUTE_TILE / n * 9 / 8 + 1024, 65520));
+        p.json_cap = (uint32_t)align16(std::min<uint64_t>(tot[1] * JUTE_TILE / n * 9 / 8 + 1024, 65520));  /* lengths travel as 16 bits */
+        p.path_limit = tot[0] + 16;                 /* every stream buffer of this library has >= 16 bytes of slack */
+        p.json_limit = tot[1] + 16;
+        /* ... + one owner byte per 16-byte output block of a tile that fits the staging budgets */
+        const size_t owner_bytes = (p.path_cap + p.json_cap + JUTE_FIXED * JUTE_TILE) / 16 + 32;
+        const size_t smem = 34 * 16 + 16 + JUTE_TILE * 20 + 16 + 32 + 16 + (size_t)p.path_cap + 16 + p.json_cap + 48 + owner_bytes;
         static std::mutex mu;
         static size_t high[64];
         {
