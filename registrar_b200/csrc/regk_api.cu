@@ -1881,8 +1881,25 @@ int regk_decode(regk_ctx *ctx, const regk_decode_in *in, regk_decode_out *out)
         p.out = (Decoded *)ctx->dec_rec.p;
         p.dom_bytes = (uint8_t *)ctx->dec_dom.p;
         p.ports = (uint32_t *)ctx->dec_ports.p;
+        /* staging budgets: 9/8 of a tile's mean share of each stream plus slack; streams handed in by the caller
+           carry no slack behind their last byte, the library's own buffers have >= 16 bytes */
+        p.path_cap = (uint32_t)align16(std::min<uint64_t>(path_total * DEC_TILE / n * 9 / 8 + 1024, 49152));
+        p.json_cap = (uint32_t)align16(std::min<uint64_t>(json_total * DEC_TILE / n * 9 / 8 + 1024, 65536));
+        const uint64_t slack = (in_dev && !last) ? 0 : 16;     /* a caller's own device buffers end where they end */
+        p.path_limit = path_total + slack;
+        p.json_limit = json_total + slack;
+        const size_t dsmem = 2 * ((size_t)p.path_cap + 32) + p.json_cap + 32 + DEC_TILE * sizeof(Decoded) + 16;
+        {
+            static std::mutex mu;
+            static size_t high[64];
+            std::lock_guard<std::mutex> lock(mu);
+            if (dsmem > high[ctx->device & 63]) {
+                CK(cudaFuncSetAttribute(regk_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem));
+                high[ctx->device & 63] = dsmem;
+            }
+        }
         CK(cudaEventRecord(e0, s));
-        regk_decode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+        regk_decode_kernel<<<(unsigned)((n + DEC_TILE - 1) / DEC_TILE), DEC_TILE, dsmem, s>>>(p);
         CK(cudaGetLastError());
         CK(cudaEventRecord(e1, s));
         out->launches = 1;
