@@ -1751,7 +1751,7 @@ int regk_jute_frames(regk_ctx *ctx, uint32_t flags, int32_t xid_base, uint32_t z
         p.path_limit = tot[0] + 16;                 /* every stream buffer of this library has >= 16 bytes of slack */
         p.json_limit = tot[1] + 16;
         /* ... + one owner byte per 16-byte output block of a tile that fits the staging budgets */
-        const size_t owner_bytes = (p.path_cap + p.json_cap + JUTE_FIXED * JUTE_TILE) / 16 + 32;
+        const size_t owner_bytes = 3 * ((p.path_cap + p.json_cap + JUTE_FIXED * JUTE_TILE) / 16 + 32);   /* owner u8 + list u16 per block */
         const size_t smem = 34 * 16 + 16 + JUTE_TILE * 20 + 16 + 32 + 16 + (size_t)p.path_cap + 16 + p.json_cap + 48 + owner_bytes;
         static std::mutex mu;
         static size_t high[64];

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_foff[JUTE_TILE + 1], s_poff[JUTE_TILE + 1], s_joff[JUTE_TILE + 1];
+    __shared__ uint32_t s_nlist;
     __shared__ uint4 s_rec[JUTE_TILE];                          /* {frame offset, path offset, payload offset, P | J << 16} */
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint64_t r0 = (uint64_t)blockIdx.x * JUTE_TILE;
@@ -224,7 +225,36 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
     mbar_wait(&s_bar, 0);
     __syncthreads();
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(smem);
+    /* Phase 1: blocks that lie entirely inside ONE path or payload segment (about 70 % of them) are a straight
+       realigned copy - no masks, no segment walk, every lane busy; the others are only listed.  Phase 2 takes the
+       list, compacted, through the general walk - so the lanes of a warp no longer wait for the one block that
+       straddles three segments. */
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_owner + ((nblk + 15u) & ~15u));
+    if (t == 0)
+        s_nlist = 0;
+    __syncthreads();
     for (uint32_t b = t; b < nblk; b += JUTE_THREADS) {
+        const int32_t bstart = (int32_t)(16u * b) - (int32_t)lead;
+        const uint32_t i = s_owner[b];
+        const uint4 rc = s_rec[i];
+        const uint32_t fo = (uint32_t)bstart - rc.x;            /* meaningful when bstart >= 0 */
+        const uint32_t P = rc.w & 0xFFFFu, J = rc.w >> 16;
+        const bool whole = bstart >= 0 && (uint32_t)bstart + 16u <= total;
+        const bool in_path = fo >= JUTE_HEAD && fo + 16u <= JUTE_HEAD + P;
+        const bool in_data = fo >= JUTE_HEAD + P + 4u && fo + 16u <= JUTE_HEAD + P + 4u + J;
+        if (whole && (in_path || in_data)) {
+            const uint32_t src = in_path ? rc.y + (fo - JUTE_HEAD) : rc.z + (fo - JUTE_HEAD - P - 4u);
+            uint32_t v[4];
+            load16(sw, src, v);
+            stg_v4(p.out_bytes + a0 + 16ull * b, make_uint4(v[0], v[1], v[2], v[3]));
+        } else {
+            s_list[atomicAdd(&s_nlist, 1u)] = (uint16_t)b;
+        }
+    }
+    __syncthreads();
+    const uint32_t nlist = s_nlist;
+    for (uint32_t li = t; li < nlist; li += JUTE_THREADS) {
+        const uint32_t b = s_list[li];
         const int32_t bstart = (int32_t)(16u * b) - (int32_t)lead;     /* tile-relative frame byte of the block's byte 0 */
         uint32_t pos = bstart < 0 ? 0u : (uint32_t)bstart;
         const uint32_t end = min((uint32_t)(bstart + 16), total);
