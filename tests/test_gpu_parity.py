@@ -552,6 +552,44 @@ def test_pipelined_errors_carry_global_record_indices(small_chunks):
 
 # ---- BASELINE.json full sizes (configs[2] 10M records; the per-GPU share of configs[4] 100M/8) ---------------
 
+def _round_trip_and_frames(ctx, batch, got):
+    import struct
+    from registrar_b200 import _native as nv
+    m = batch.n
+    rec, dom, ports, _ = ctx.decode(last=True, host_nodes=True)
+    assert len(rec) == m and np.all(rec["flags"] == (nv.DEC_PATH_OK | nv.DEC_HOST_RECORD))
+    assert np.array_equal(rec["dom_len"], np.diff(batch.domain_off.astype(np.int64)))
+    assert np.all(rec["host_len"] == batch.host_stride)
+    assert np.array_equal(rec["ttl"], batch.ttl)
+    k = np.diff(batch.ports_off.astype(np.int64))
+    assert np.array_equal(np.where(rec["nports"] == 0xFFFFFFFF, 0, rec["nports"]).astype(np.int64), k)
+    # every port value: slot i holds record i's ports at element json_off[i] / 2
+    has = k > 0
+    first = (got.json_off[:-1][has] >> np.uint64(1)).astype(np.int64)
+    assert np.array_equal(ports[first], batch.ports[batch.ports_off[:-1][has].astype(np.int64)])
+    for i in range(0, m, max(1, m // 64)):
+        a = int(got.path_off[i])
+        assert bytes(dom[a:a + int(rec["dom_len"][i])]) == batch.record(i)["domain"].lower()
+    fb, fo, _ = ctx.jute_frames(xid_base=7, zk_flags=1)
+    assert np.array_equal(fo, got.path_off + got.json_off + np.uint64(51) * np.arange(m + 1, dtype=np.uint64))
+    for i in range(0, m, max(1, m // 64)):
+        f = bytes(fb[int(fo[i]):int(fo[i + 1])])
+        p, j = got.path(i), got.json(i)
+        assert f[:16] == struct.pack(">iiii", len(f) - 4, 7 + i, 1, len(p)) and f[16:16 + len(p)] == p
+        assert f[16 + len(p):20 + len(p)] == struct.pack(">i", len(j)) and f[20 + len(p):20 + len(p) + len(j)] == j
+        assert f[-31:] == struct.pack(">ii", 1, 31) + struct.pack(">i", 5) + b"world" + struct.pack(">i", 6) + b"anyone" + struct.pack(">i", 1)
+    # the frames carry every path and payload byte exactly once: a checksum of checksums
+    assert int(fo[-1]) == int(got.path_off[-1]) + int(got.json_off[-1]) + 51 * m
+    # byte sum of all frames = byte sums of both streams + the framing bytes (constants: acl 27 bytes + flags; per
+    # frame: the big-endian bytes of length, xid, opcode, path length, data length)
+    be = lambda v: (v & 255) + ((v >> 8) & 255) + ((v >> 16) & 255) + ((v >> 24) & 255)
+    P = np.diff(got.path_off.astype(np.int64)); J = np.diff(got.json_off.astype(np.int64))
+    framing = be(P + J + 47).sum() + be(7 + np.arange(m, dtype=np.int64)).sum() + m * 1 + be(P).sum() + be(J).sum() + \
+        m * (1 + 31 + 5 + sum(b"world") + 6 + sum(b"anyone") + 1)
+    assert int(fb.astype(np.uint64).sum()) == int(got.path_bytes.astype(np.uint64).sum()) + \
+        int(got.json_bytes.astype(np.uint64).sum()) + int(framing)
+
+
 def _chunked_compare(ctx, config, n, chunk, start=0):
     """bit-exact against the oracle, chunk by chunk (bounds host memory), plus stream-level invariants"""
     import zlib
@@ -569,6 +607,9 @@ def _chunked_compare(ctx, config, n, chunk, start=0):
         # invariants that do not need the oracle: closed-form path size, monotone offsets
         assert int(got.path_off[-1]) == int(batch.domain_off[-1]) + m * (36 + 2)
         assert np.all(np.diff(got.json_off.astype(np.int64)) >= 42)
+        # the rows either side of the path, on the same batch at full chunk size: decode(encode(x)) == x (lengths, ttl,
+        # port counts for every record; bytes for a sample) and the wire frames' closed-form layout
+        _round_trip_and_frames(ctx, batch, got)
         p_total += int(got.path_off[-1])
         j_total += int(got.json_off[-1])
         crc_p = zlib.crc32(got.path_bytes.tobytes(), crc_p)
