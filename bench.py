@@ -25,7 +25,8 @@ config 3 (2-6 labels, 75 % with 1-4 SRV ports), the largest single-GPU entry of 
          ~1.2 GB each, far larger than the 126 MB L2) are rotated.
   e2e    the same metric through the public call a user makes (Context.submit / collect = the C-ABI
          regk_register_batch with HOST buffers): pinned host inputs -> H2D -> kernels -> D2H of paths, payloads
-         and both offset arrays, every step, wall clock between barriers (each rank its shard when N > 1).
+         and both offset arrays (as 32-bit arrays: option "offsets32"), every step, wall clock between barriers
+         (each rank its shard when N > 1).
   roofline   per kernel: algorithmic bytes per launch / mean launch duration (CUDA events recorded by the
          library around each launch inside the timed region), against MEASURED_PEAKS.json hbm_gbs.
   check  outside the timed regions the outputs of the timed configuration are fingerprinted on the GPU
@@ -386,6 +387,7 @@ def e2e_loop(rig, pinned, steps, depth=2):
     """Host buffers in, host buffers out, `depth` batches in flight; wall clock between barriers."""
     ctx, torch = rig.ctx, rig.torch
     ctx.set_option("async", 1)
+    ctx.set_option("offsets32", 1)           # host results with 32-bit offsets: both streams are far below 4 GiB
     res = None
     for i in range(2):
         res = ctx.collect(ctx.submit(pinned[i % len(pinned)]))
@@ -407,6 +409,7 @@ def e2e_loop(rig, pinned, steps, depth=2):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     ctx.set_option("async", 0)
+    ctx.set_option("offsets32", 0)
     rig.sampler.active.clear()
     rig.barrier()
     return dt, h2d, d2h
@@ -466,7 +469,7 @@ def measure_single(rig, cfg, n, start, steps, warmup, e2e_steps, time_every, ver
                           "what": "algorithmic bytes of both kernels / whole step time (launch gaps included)"},
         "e2e": {"value": n * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "api": "registrar_b200.Context.submit/collect -> regk_register_batch (host buffers)"},
+                "api": "registrar_b200.Context.submit/collect -> regk_register_batch (host buffers, option offsets32)"},
         "gpu_launches": stats["launches"], "verified": verified,
         "generic_tiles": {"per_step": stats["generic_tiles"], "of": 2 * ((n + 127) // 128),
                           "what": "tiles (128 records, both kernels) that outgrew the shared-memory budget and were composed in global memory"},

@@ -139,6 +139,10 @@ typedef struct regk_result {
     uint32_t        generic_tiles;  /* tiles (128 records, counted per kernel) that did not fit the kernels' shared-memory
                                        budget and were composed straight from / to global memory (about 10x slower) */
     uint32_t        reserved;
+    /* option "offsets32" = 1 (host results only, both streams below 4 GiB): the offsets come back as 32-bit arrays
+       - half the device-to-host bytes of the two offset arrays - and path_off / json_off are NULL */
+    uint32_t       *path_off32;     /* [n+1] */
+    uint32_t       *json_off32;     /* [n+1] */
 } regk_result;
 
 /* ---- lifecycle ----------------------------------------------------------- */

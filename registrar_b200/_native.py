@@ -60,7 +60,8 @@ class CResult(C.Structure):          # regk_result
                 ("json_len_kernel_ms", C.c_float), ("launches", C.c_uint32), ("opaque", C.c_void_p),
                 ("job_path_base", C.c_uint64), ("job_path_total", C.c_uint64),
                 ("job_json_base", C.c_uint64), ("job_json_total", C.c_uint64),
-                ("generic_tiles", C.c_uint32), ("reserved", C.c_uint32)]
+                ("generic_tiles", C.c_uint32), ("reserved", C.c_uint32),
+                ("path_off32", C.c_void_p), ("json_off32", C.c_void_p)]
 
 
 MAX_PEERS = 16
@@ -235,6 +236,12 @@ class HostResult:
         return bytes(self.json_bytes[int(self.json_off[i]):int(self.json_off[i + 1])])
 
 
+def _offsets(res, which: str, n: int):
+    """The offset array of a finished host result: uint64, or uint32 under option "offsets32"."""
+    p32 = getattr(res, which + "32")
+    return _as_np(p32, n + 1, np.uint32) if p32 else _as_np(getattr(res, which), n + 1, np.uint64)
+
+
 def _as_np(ptr, count, dtype):
     if count == 0 or not ptr:
         return np.zeros(0, dtype)
@@ -322,8 +329,8 @@ class Context:
         n = int(res.n)
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
         out = HostResult(
-            n, cp(_as_np(res.path_bytes, int(res.path_total), np.uint8)), cp(_as_np(res.path_off, n + 1, np.uint64)),
-            cp(_as_np(res.json_bytes, int(res.json_total), np.uint8)), cp(_as_np(res.json_off, n + 1, np.uint64)),
+            n, cp(_as_np(res.path_bytes, int(res.path_total), np.uint8)), cp(_offsets(res, "path_off", n)),
+            cp(_as_np(res.json_bytes, int(res.json_total), np.uint8)), cp(_offsets(res, "json_off", n)),
             float(res.kernel_ms), float(res.path_kernel_ms), float(res.json_kernel_ms), int(res.launches),
             float(res.json_len_kernel_ms), int(res.generic_tiles))
         self._lib.regk_release(self._h, C.byref(res))
@@ -410,8 +417,8 @@ class Context:
         n = int(res.n)
         cp = (lambda a: a.copy()) if copy else (lambda a: a)
         out = HostResult(
-            n, cp(_as_np(res.path_bytes, int(res.path_total), np.uint8)), cp(_as_np(res.path_off, n + 1, np.uint64)),
-            cp(_as_np(res.json_bytes, int(res.json_total), np.uint8)), cp(_as_np(res.json_off, n + 1, np.uint64)),
+            n, cp(_as_np(res.path_bytes, int(res.path_total), np.uint8)), cp(_offsets(res, "path_off", n)),
+            cp(_as_np(res.json_bytes, int(res.json_total), np.uint8)), cp(_offsets(res, "json_off", n)),
             float(res.kernel_ms), float(res.path_kernel_ms), float(res.json_kernel_ms), int(res.launches),
             float(res.json_len_kernel_ms), int(res.generic_tiles))
         self._lib.regk_release(self._h, C.byref(res))

@@ -63,7 +63,7 @@ struct regk_ctx {
     /* device staging of host batches */
     DevBuf in[11];
     /* outputs */
-    DevBuf path_bytes, path_off, json_bytes, json_off;
+    DevBuf path_bytes, path_off, json_bytes, json_off, off32_p, off32_j;
     HostBuf h_path_bytes, h_path_off, h_json_bytes, h_json_off, h_running;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;          /* host pipelining (run_pipelined, two-deep async) */
     /* "async" host batches alternate between two complete sets of staging, device outputs and pinned result
@@ -71,7 +71,7 @@ struct regk_ctx {
        finished, whichever comes first - the copy sizes are only known once k's kernels are done) */
     struct HostSet {
         DevBuf in[11];
-        DevBuf path_bytes, path_off, json_bytes, json_off;
+        DevBuf path_bytes, path_off, json_bytes, json_off, off32_p, off32_j;
         HostBuf h_path_bytes, h_path_off, h_json_bytes, h_json_off;
         cudaEvent_t e_in = nullptr, e_out = nullptr;
     };
@@ -143,6 +143,7 @@ struct regk_ctx {
         uint32_t host_stride = 0;
         bool alias = false;
         bool job = false;                       /* a REGK_JOB_STEP batch */
+        bool off32 = false;                     /* host results with 32-bit offsets (option "offsets32") */
         uint64_t json_est = 0;                  /* a-priori payload bytes per record of this batch */
         bool json_learned = false;              /* its image budget came from json_mean_seen */
         bool in_use = false;
@@ -247,6 +248,24 @@ bool smem_attr_needs_raise(int device, int which, size_t bytes)
 }
 
 }  // namespace
+
+/* "offsets32": host results carry 32-bit offsets (half the D2H bytes of the two offset arrays) */
+__global__ void __launch_bounds__(256) regk_off32_kernel(const unsigned long long *__restrict__ src, uint32_t *__restrict__ dst, uint64_t n1)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n1)
+        dst[i] = (uint32_t)src[i];
+}
+
+static int narrow_offsets(regk_ctx *ctx, const void *src64, DevBuf &dst32, uint64_t n, cudaStream_t s)
+{
+    int rc = ensure_dev(ctx, dst32, (n + 1) * 4);
+    if (rc)
+        return rc;
+    regk_off32_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>((const unsigned long long *)src64, (uint32_t *)dst32.p, n + 1);
+    CK(cudaGetLastError());
+    return REGK_OK;
+}
 
 /*
  * Host buffers in, host buffers out, large batch: the PCIe copies dominate (config 2: 91 MB in, 171 MB out
@@ -501,15 +520,17 @@ static int issue_d2h(regk_ctx *ctx, regk_ctx::Slot &slot)
         (rc = ensure_host(ctx, hs.h_json_bytes, st.json_total + 16)) || (rc = ensure_host(ctx, hs.h_json_off, (n + 1) * 8)))
         return rc;
     cudaStream_t sd = ctx->s_d2h;
+    slot.off32 = slot.off32 && st.path_total < (1ull << 32) && st.json_total < (1ull << 32);   /* else: 64-bit after all */
+    const size_t ow = slot.off32 ? 4 : 8;
     if (n && do_path) {
         CK(cudaMemcpyAsync(hs.h_path_bytes.p, hs.path_bytes.p, st.path_total, cudaMemcpyDeviceToHost, sd));
-        CK(cudaMemcpyAsync(hs.h_path_off.p, hs.path_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, sd));
+        CK(cudaMemcpyAsync(hs.h_path_off.p, slot.off32 ? hs.off32_p.p : hs.path_off.p, (n + 1) * ow, cudaMemcpyDeviceToHost, sd));
     } else {
         memset(hs.h_path_off.p, 0, (n + 1) * 8);
     }
     if (n && do_json) {
         CK(cudaMemcpyAsync(hs.h_json_bytes.p, hs.json_bytes.p, st.json_total, cudaMemcpyDeviceToHost, sd));
-        CK(cudaMemcpyAsync(hs.h_json_off.p, hs.json_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, sd));
+        CK(cudaMemcpyAsync(hs.h_json_off.p, slot.off32 ? hs.off32_j.p : hs.json_off.p, (n + 1) * ow, cudaMemcpyDeviceToHost, sd));
     } else {
         memset(hs.h_json_off.p, 0, (n + 1) * 8);
     }
@@ -588,7 +609,8 @@ void regk_destroy(regk_ctx *ctx)
     for (auto &b : ctx->in)
         if (b.p)
             cudaFree(b.p);
-    for (DevBuf *b : {&ctx->blob_dev, &ctx->path_bytes, &ctx->path_off, &ctx->json_bytes, &ctx->json_off, &ctx->work})
+    for (DevBuf *b : {&ctx->blob_dev, &ctx->path_bytes, &ctx->path_off, &ctx->json_bytes, &ctx->json_off, &ctx->work, &ctx->off32_p,
+             &ctx->off32_j})
         if (b->p)
             cudaFree(b->p);
     for (cudaEvent_t e : ctx->pipe_events)
@@ -601,7 +623,7 @@ void regk_destroy(regk_ctx *ctx)
         for (auto &b : hs.in)
             if (b.p)
                 cudaFree(b.p);
-        for (DevBuf *b : {&hs.path_bytes, &hs.path_off, &hs.json_bytes, &hs.json_off})
+        for (DevBuf *b : {&hs.path_bytes, &hs.path_off, &hs.json_bytes, &hs.json_off, &hs.off32_p, &hs.off32_j})
             if (b->p)
                 cudaFree(b->p);
         for (HostBuf *b : {&hs.h_path_bytes, &hs.h_path_off, &hs.h_json_bytes, &hs.h_json_off})
@@ -680,7 +702,7 @@ int regk_set_option(regk_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name)
         return REGK_ERR_INVALID_ARG;
-    static const char *known[] = {"async", "force_generic", "dom_cap", "json_out_cap", "chunk_records", "time_every", nullptr};
+    static const char *known[] = {"async", "force_generic", "dom_cap", "json_out_cap", "chunk_records", "time_every", "offsets32", nullptr};
     for (const char **k = known; *k; k++)
         if (!strcmp(*k, name)) {
             ctx->opt[name] = value;
@@ -1354,6 +1376,13 @@ int regk_register_batch(regk_ctx *ctx, const regk_batch *b, regk_result *res)
     } else if (timed) {
         CK(cudaEventRecord(slot.ev[2], s));
     }
+    slot.off32 = !out_dev && !job && n && opt_get(ctx, "offsets32", 0) != 0;
+    if (slot.off32) {
+        if (do_path && (rc = narrow_offsets(ctx, o_path_off.p, hs ? hs->off32_p : ctx->off32_p, n, s)))
+            return rc;
+        if (do_json && (rc = narrow_offsets(ctx, o_json_off.p, hs ? hs->off32_j : ctx->off32_j, n, s)))
+            return rc;
+    }
     CK(cudaEventRecord(slot.ev[3], s));
     if (job) {
         /* exchange 3 (closing barrier): once it has passed, every rank's tiles and offsets are in this rank's buffers */
@@ -1461,6 +1490,11 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
         else
             regk_path_kernel<false, true><<<ntiles_r, TILE, slot->path_smem, s>>>(p, JsonParams{});
         CK(cudaGetLastError());
+        if (slot->off32) {
+            int rc2 = narrow_offsets(ctx, p.out_off, slot->hset >= 0 ? ctx->hset[slot->hset].off32_p : ctx->off32_p, p.n, s);
+            if (rc2)
+                return rc2;
+        }
         CK(cudaMemcpyAsync(slot->h_status, slot->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
         e = cudaStreamSynchronize(s);
         if (e != cudaSuccess)
@@ -1544,33 +1578,45 @@ int regk_finish(regk_ctx *ctx, regk_result *res)
             return fail(ctx, REGK_ERR_CUDA, "device-to-host copy failed: %s", cudaGetErrorString(e));
         res->flags = 0;
         res->path_bytes = (uint8_t *)hs.h_path_bytes.p;
-        res->path_off = (uint64_t *)hs.h_path_off.p;
         res->json_bytes = (uint8_t *)hs.h_json_bytes.p;
-        res->json_off = (uint64_t *)hs.h_json_off.p;
+        if (slot->off32) {
+            res->path_off32 = (uint32_t *)hs.h_path_off.p;
+            res->json_off32 = (uint32_t *)hs.h_json_off.p;
+        } else {
+            res->path_off = (uint64_t *)hs.h_path_off.p;
+            res->json_off = (uint64_t *)hs.h_json_off.p;
+        }
         return REGK_OK;
     }
     const bool do_path = !(slot->flags & REGK_NO_PATH), do_json = !(slot->flags & REGK_NO_JSON);
     if ((rc = ensure_host(ctx, ctx->h_path_bytes, st.path_total + 16)) || (rc = ensure_host(ctx, ctx->h_path_off, (n + 1) * 8)) ||
         (rc = ensure_host(ctx, ctx->h_json_bytes, st.json_total + 16)) || (rc = ensure_host(ctx, ctx->h_json_off, (n + 1) * 8)))
         return rc;
+    slot->off32 = slot->off32 && st.path_total < (1ull << 32) && st.json_total < (1ull << 32);
+    const size_t ow = slot->off32 ? 4 : 8;
     if (n && do_path) {
         CK(cudaMemcpyAsync(ctx->h_path_bytes.p, ctx->path_bytes.p, st.path_total, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_path_off.p, ctx->path_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_path_off.p, slot->off32 ? ctx->off32_p.p : ctx->path_off.p, (n + 1) * ow, cudaMemcpyDeviceToHost, s));
     } else {
         memset(ctx->h_path_off.p, 0, (n + 1) * 8);
     }
     if (n && do_json) {
         CK(cudaMemcpyAsync(ctx->h_json_bytes.p, ctx->json_bytes.p, st.json_total, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_json_off.p, ctx->json_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_json_off.p, slot->off32 ? ctx->off32_j.p : ctx->json_off.p, (n + 1) * ow, cudaMemcpyDeviceToHost, s));
     } else {
         memset(ctx->h_json_off.p, 0, (n + 1) * 8);
     }
     CK(cudaStreamSynchronize(s));
     res->flags = 0;
     res->path_bytes = (uint8_t *)ctx->h_path_bytes.p;
-    res->path_off = (uint64_t *)ctx->h_path_off.p;
     res->json_bytes = (uint8_t *)ctx->h_json_bytes.p;
-    res->json_off = (uint64_t *)ctx->h_json_off.p;
+    if (slot->off32) {
+        res->path_off32 = (uint32_t *)ctx->h_path_off.p;
+        res->json_off32 = (uint32_t *)ctx->h_json_off.p;
+    } else {
+        res->path_off = (uint64_t *)ctx->h_path_off.p;
+        res->json_off = (uint64_t *)ctx->h_json_off.p;
+    }
     return REGK_OK;
 }
 

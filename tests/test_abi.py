@@ -54,7 +54,7 @@ def test_struct_layouts_match_header(built):
                offsetof(regk_decode_in, json_off), sizeof(regk_decode_out), offsetof(regk_decode_out, ports),
                offsetof(regk_decode_out, kernel_ms));
         printf("%zu %zu %zu %zu %zu ", sizeof(regk_job), offsetof(regk_job, mailbox), offsetof(regk_job, timeout_ms),
-               offsetof(regk_result, job_path_base), offsetof(regk_result, job_json_total));
+               offsetof(regk_result, job_path_base), offsetof(regk_result, json_off32));
         printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(regk_batch), offsetof(regk_batch, domain_bytes),
                offsetof(regk_batch, ports_present), sizeof(regk_result), offsetof(regk_result, json_total),
                offsetof(regk_result, opaque), sizeof(regk_gather), offsetof(regk_gather, totals),
@@ -71,7 +71,7 @@ def test_struct_layouts_match_header(built):
            _native.CDecodeIn.json_off.offset, C.sizeof(_native.CDecodeOut), _native.CDecodeOut.ports.offset,
            _native.CDecodeOut.kernel_ms.offset,
            C.sizeof(_native.CJob), _native.CJob.mailbox.offset, _native.CJob.timeout_ms.offset,
-           _native.CResult.job_path_base.offset, _native.CResult.job_json_total.offset,
+           _native.CResult.job_path_base.offset, _native.CResult.json_off32.offset,
            C.sizeof(_native.CBatch), _native.CBatch.domain_bytes.offset, _native.CBatch.ports_present.offset,
            C.sizeof(_native.CResult), _native.CResult.json_total.offset, _native.CResult.opaque.offset,
            C.sizeof(_native.CGather), _native.CGather.totals.offset, _native.CGather.json_off.offset,

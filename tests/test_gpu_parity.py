@@ -268,6 +268,36 @@ def test_corrupt_offsets_on_the_pipelined_host_path(ctx):
         ctx.set_option("chunk_records", 262144)
 
 
+def test_offsets32_option(ctx):
+    """option "offsets32": host results with 32-bit offsets (half the D2H bytes of the offset arrays) - same numbers,
+    sync and two-deep async, with and without the exact-offset redo, either half alone."""
+    ctx.set_option("offsets32", 1)
+    try:
+        for cfg, n in (("config3", 30011), ("config2", 1), ("config5", 5000)):
+            batch = synth.generate(cfg, n=n)
+            got = ctx.register_batch(batch)
+            assert got.path_off.dtype == np.uint32 and got.json_off.dtype == np.uint32
+            assert_same(got, oracle.register_batch(batch))
+        recs = [{"domain": b"a%d..b.c" % i if i % 50 == 7 else b"a%d.b.c" % i, "hostname": b"h%d" % i, "type": b"host",
+                 "address": b"10.0.0.%d" % (i % 250)} for i in range(700)]
+        batch = RecordBatch.from_records(recs)
+        assert_same(ctx.register_batch(batch), oracle.register_batch(batch))         # empty labels: offsets redone
+        got = ctx.register_batch(batch, payloads=False)
+        assert np.array_equal(got.path_off, oracle.register_batch(batch).path_off) and got.json_total == 0
+        ctx.set_option("async", 1)
+        b1, b2 = synth.generate("config3", n=4000, start=5), synth.generate("config2", n=3000, start=9)
+        t1 = ctx.submit(b1); t2 = ctx.submit(b2)
+        for t, b in ((t1, b1), (t2, b2)):
+            got = ctx.collect(t, copy=True)
+            assert got.path_off.dtype == np.uint32
+            assert_same(got, oracle.register_batch(b))
+    finally:
+        ctx.set_option("async", 0)
+        ctx.set_option("offsets32", 0)
+    got = ctx.register_batch(synth.generate("config1"))
+    assert got.path_off.dtype == np.uint64
+
+
 def test_short_last_tile_at_every_output_phase(ctx):
     """A last tile holding one short record (17..30 path bytes, no aligned 16-byte block inside) at every
     byte phase of the output stream, for tile sizes 64/128/256: only head/tail byte stores, no bulk body."""
