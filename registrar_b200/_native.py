@@ -378,7 +378,10 @@ class Context:
         """regk_decode over explicit host streams (uint8 bytes + uint64 CSR offsets) or, with last=True, over the
         batch finished last on this context.  Returns (rec: structured array of regk_decoded, dom_bytes in slot
         layout, ports in slot layout, kernel_ms)."""
-        keep = [None if a is None else np.ascontiguousarray(a) for a in (path_bytes, path_off, json_bytes, json_off)]
+        keep = [None if path_bytes is None else np.ascontiguousarray(path_bytes, dtype=np.uint8),
+                None if path_off is None else np.ascontiguousarray(path_off, dtype=np.uint64),    # also accepts 32-bit offsets
+                None if json_bytes is None else np.ascontiguousarray(json_bytes, dtype=np.uint8),
+                None if json_off is None else np.ascontiguousarray(json_off, dtype=np.uint64)]
         n = 0
         for off in (keep[1], keep[3]):
             if off is not None:
