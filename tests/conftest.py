@@ -33,7 +33,8 @@ def emul(built):
     so = os.path.join(ROOT, "tests", "emul", "libregemul.so")
     srcs = [os.path.join(ROOT, "tests", "emul", "emul.cpp"),
             os.path.join(ROOT, "registrar_b200", "csrc", "regk_core.cuh"),
-            os.path.join(ROOT, "registrar_b200", "csrc", "regk_types.hpp")]
+            os.path.join(ROOT, "registrar_b200", "csrc", "regk_types.hpp"),
+            os.path.join(ROOT, "registrar_b200", "csrc", "regk_decode_core.cuh")]
     if not _newer(so, *srcs):
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
                                "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-o", so, srcs[0]])
@@ -43,6 +44,7 @@ def emul(built):
     lib.emul_build_blob.restype = C.c_int
     lib.emul_parents.restype = C.c_uint64
     lib.emul_services.restype = C.c_uint64
+    lib.emul_decode.restype = None
     return lib
 
 

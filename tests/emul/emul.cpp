@@ -17,6 +17,7 @@
 
 #include "../../include/regk.h"
 #include "../../registrar_b200/csrc/regk_core.cuh"
+#include "../../registrar_b200/csrc/regk_decode_core.cuh"
 
 using namespace regk;
 
@@ -374,3 +375,25 @@ extern "C" uint64_t emul_services(uint64_t n, const uint8_t *srvce_bytes, const 
     out_off[n] = base;
     return 0;
 }
+
+/* the reader side's per-record logic (regk_decode_core.cuh) on the host: out = n records of 10 uint32 words, domains in
+   slot layout (domain i at path_off[i]), ports in slot layout (element json_off[i] / 2) */
+extern "C" void emul_decode(uint64_t n, const uint8_t *path_bytes, const uint64_t *path_off, const uint8_t *json_bytes,
+    const uint64_t *json_off, int host_nodes, uint32_t *out, uint8_t *dom_bytes, uint32_t *ports)
+{
+    for (uint64_t r = 0; r < n; r++) {
+        Decoded d;
+        d.flags = 0;
+        d.dom_len = d.host_pos = d.host_len = d.type_pos = d.type_len = d.addr_pos = d.addr_len = 0;
+        d.ttl = INT32_MIN;
+        d.nports = 0xFFFFFFFFu;
+        if (path_bytes)
+            d.flags |= decode_path(path_bytes + path_off[r], (uint32_t)(path_off[r + 1] - path_off[r]), host_nodes != 0,
+                dom_bytes + path_off[r], d);
+        if (json_bytes)
+            d.flags |= decode_payload(json_bytes + json_off[r], (uint32_t)(json_off[r + 1] - json_off[r]), d,
+                ports + (json_off[r] >> 1));
+        memcpy(out + 10 * r, &d, sizeof d);
+    }
+}
+
