@@ -77,6 +77,43 @@ function registerBatch(records, cb) {
 }
 
 /*
+ * N `registration.service` objects -> the payloads of their service records (lib/register.js:45-75), one GPU call.
+ * The inner object's key order is kept (JSON.stringify follows insertion order); a missing ttl is 60 and goes last,
+ * as the assignment at lib/register.js:197 leaves it.
+ */
+var SERVICE_KEYS = [ 'srvce', 'proto', 'port', 'ttl' ];
+
+function servicePayloads(services, cb) {
+    var n = services.length, port = Buffer.alloc(4 * n), ttl = Buffer.alloc(4 * n), order = Buffer.alloc(n);
+    var srv = [], pro = [];
+    services.forEach(function (s, i) {
+        assert.ok(s.type === 'service');
+        var inner = s.service, keys = Object.keys(inner).filter(function (k) { return (k !== 'ttl' || inner.ttl !== undefined); });
+        keys.forEach(function (k) {
+            if (SERVICE_KEYS.indexOf(k) === -1)
+                throw (new RangeError('service ' + i + ': member ' + k + ' is outside the supported domain'));
+        });
+        if (keys.indexOf('ttl') === -1)
+            keys.push('ttl');
+        var t = inner.ttl !== undefined ? inner.ttl : 60;
+        if (!Number.isInteger(inner.port) || inner.port < 0 || inner.port > 4294967295 || !Number.isInteger(t) ||
+            t < -2147483648 || t > 2147483647)
+            throw (new RangeError('service ' + i + ': port / ttl outside the supported domain (integers)'));
+        srv.push(inner.srvce);
+        pro.push(inner.proto);
+        port.writeUInt32LE(inner.port, 4 * i);
+        ttl.writeInt32LE(t, 4 * i);
+        order[i] = keys.reduce(function (acc, k, j) { return (acc | (SERVICE_KEYS.indexOf(k) << (2 * j))); }, 0);
+    });
+    var s1 = packStrings(srv), p1 = packStrings(pro);
+    regk.serviceRecords({ n: n, srvceBytes: s1.bytes, srvceOff: s1.off, protoBytes: p1.bytes, protoOff: p1.off, port: port,
+        ttl: ttl, keyOrder: order }, function (err, res) {
+        if (err) { cb(err); return; }
+        cb(null, slices(res.jsonBytes, res.jsonOff, n));
+    });
+}
+
+/*
  * The argument contract of register(opts, cb) — reference lib/register.js:175-201 — as data: one row per
  * check, [assert-plus method, path below `options`, only-if path].  Rows run in order, so the first failing
  * check raises the same AssertionError (same method, same label) as the reference does.  Two entries are not
@@ -155,6 +192,9 @@ function register(opts, cb) {
                 },
                 function service(c, next) {
                     if (!reg.service) { next(); return; }
+                    /* zk.put(path, obj, cb) has no options argument to flag pre-serialised bytes with, so the
+                       object goes to the client as in the reference; servicePayloads() is the batched GPU route
+                       (the Python mirror, whose client accepts bytes, uses it inside register()) */
                     zk.put(c.path, { type: 'service', service: reg.service }, function (e) {
                         if (!e && c.nodes.indexOf(c.path) === -1) c.nodes.push(c.path);
                         next(e);
@@ -171,4 +211,4 @@ function firstAddress() {
     return (ifaces[k][0].address);
 }
 
-module.exports = { register: register, registerBatch: registerBatch };
+module.exports = { register: register, registerBatch: registerBatch, servicePayloads: servicePayloads };

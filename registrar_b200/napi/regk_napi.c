@@ -7,6 +7,8 @@
  *   regk.registerBatch({n, flags, hostStride, domainBytes, domainOff, hostBytes, hostOff?, typeId,
  *                       addrBytes, addrOff, ttl, portsOff?, ports?, portsPresent?},  // Buffers over SoA arrays
  *                      function (err, res) { res.pathBytes, res.pathOff, res.jsonBytes, res.jsonOff, res.kernelMs });
+ *   regk.serviceRecords({n, srvceBytes, srvceOff, protoBytes, protoOff, port, ttl, keyOrder?},
+ *                       function (err, res) { res.jsonBytes, res.jsonOff });          // regk_service_records
  *
  * Threading: the context is single-owner, but libuv runs queued napi_async_work items on a POOL
  * of worker threads, so two registerBatch() calls can execute at the same time.  Everything that touches the
@@ -87,6 +89,8 @@ static uint32_t u32_prop(napi_env env, napi_value obj, const char *name)
 
 typedef struct {
     regk_batch batch;
+    regk_service_batch svc;             /* serviceRecords(): this one is used instead of `batch` */
+    int is_service;
     regk_result result;
     int status;
     char error[512];
@@ -125,14 +129,15 @@ static void job_execute(napi_env env, void *data)
             g_installed = j->types;     /* identity only; the job's own reference keeps it alive while it matters */
     }
     if (j->status == REGK_OK)
-        j->status = regk_register_batch(g_ctx, &j->batch, &j->result);  /* host buffers in, pinned host buffers out */
+        j->status = j->is_service ? regk_service_records(g_ctx, &j->svc, &j->result)
+                                  : regk_register_batch(g_ctx, &j->batch, &j->result);  /* host buffers in, pinned host buffers out */
     if (j->status != REGK_OK) {
         strncpy(j->error, regk_last_error(g_ctx), sizeof j->error - 1);
     } else {
         const size_t noff = (size_t)(j->result.n + 1) * 8;
         j->path_bytes = (uint8_t *)dup_bytes(j->result.path_bytes, (size_t)j->result.path_total);
         j->json_bytes = (uint8_t *)dup_bytes(j->result.json_bytes, (size_t)j->result.json_total);
-        j->path_off = (uint64_t *)dup_bytes(j->result.path_off, noff);
+        j->path_off = j->result.path_off ? (uint64_t *)dup_bytes(j->result.path_off, noff) : (uint64_t *)calloc(1, noff);
         j->json_off = (uint64_t *)dup_bytes(j->result.json_off, noff);
         regk_release(g_ctx, &j->result);
         if (!j->path_bytes || !j->json_bytes || !j->path_off || !j->json_off) {
@@ -232,6 +237,37 @@ static napi_value register_batch(napi_env env, napi_callback_info info)
     return NULL;
 }
 
+/* serviceRecords({n, srvceBytes, srvceOff, protoBytes, protoOff, port, ttl, keyOrder?}, cb): payloads of the
+   persistent service nodes (lib/register.js:45-75) - res.jsonBytes / res.jsonOff; the paths come from registerBatch
+   with the alias flag */
+static napi_value service_records(napi_env env, napi_callback_info info)
+{
+    size_t argc = 2;
+    napi_value argv[2], name;
+    job_t *j;
+    napi_get_cb_info(env, info, &argc, argv, NULL, NULL);
+    if (argc < 2 || !g_ctx) {
+        napi_throw_error(env, NULL, "serviceRecords(batch, cb): init() first, two arguments required");
+        return NULL;
+    }
+    j = (job_t *)calloc(1, sizeof *j);
+    j->is_service = 1;
+    j->svc.n = u32_prop(env, argv[0], "n");
+    j->svc.srvce_bytes = (const uint8_t *)buf_or_null(env, argv[0], "srvceBytes", NULL);
+    j->svc.srvce_off = (const uint32_t *)buf_or_null(env, argv[0], "srvceOff", NULL);
+    j->svc.proto_bytes = (const uint8_t *)buf_or_null(env, argv[0], "protoBytes", NULL);
+    j->svc.proto_off = (const uint32_t *)buf_or_null(env, argv[0], "protoOff", NULL);
+    j->svc.port = (const uint32_t *)buf_or_null(env, argv[0], "port", NULL);
+    j->svc.ttl = (const int32_t *)buf_or_null(env, argv[0], "ttl", NULL);
+    j->svc.key_order = (const uint8_t *)buf_or_null(env, argv[0], "keyOrder", NULL);
+    napi_create_reference(env, argv[0], 1, &j->keepalive);
+    napi_create_reference(env, argv[1], 1, &j->cb);
+    napi_create_string_utf8(env, "regk_service_records", 20, &name);
+    napi_create_async_work(env, NULL, name, job_execute, job_complete, j, &j->work);
+    napi_queue_async_work(env, j->work);
+    return NULL;
+}
+
 static napi_value set_types(napi_env env, napi_callback_info info)
 {
     /* Main thread: only RECORDS the table.  It reaches the context inside the next job's job_execute, under
@@ -285,6 +321,7 @@ static napi_value module_init(napi_env env, napi_value exports)
         { "init", NULL, init_ctx, NULL, NULL, NULL, 0, NULL },
         { "setTypes", NULL, set_types, NULL, NULL, NULL, 0, NULL },
         { "registerBatch", NULL, register_batch, NULL, NULL, NULL, 0, NULL },
+        { "serviceRecords", NULL, service_records, NULL, NULL, NULL, 0, NULL },
     };
     napi_define_properties(env, exports, sizeof props / sizeof props[0], props);
     return exports;
