@@ -332,6 +332,34 @@ typedef struct regk_frames {
 int         regk_jute_frames(regk_ctx *ctx, uint32_t flags, int32_t xid_base, uint32_t zk_flags, regk_frames *out);
 
 /*
+ * The other requests of register()'s choreography, and transactions.  Same batch, same kernel, other framing:
+ *   REGK_ZK_CREATE   as regk_jute_frames (lib/register.js:156-159 create; :62 put on a node that does not exist yet)
+ *   REGK_ZK_DELETE   DeleteRequest{path, version}: the unlink list of cleanupPreviousEntries (lib/register.js:85-95)
+ *                    - one request per node path of the batch, no payload stream needed
+ *   REGK_ZK_SETDATA  SetDataRequest{path, data, version}: zkplus put() on an existing node (lib/register.js:62)
+ * group = 0: one request per record, xid = xid_base + i.  group = g >= 1: ZooKeeper multi transactions (OpCode 14) of g
+ * operations each (the last one may be shorter): frame k = len | xid_base + k | 14 | g x { MultiHeader{op, done = false,
+ * err = -1} | request body } | MultiHeader{-1, true, -1} - registering a whole fleet atomically in n / g round trips.
+ * out->n = number of frames, frame_off has n + 1 entries.  version is -1 ("any") unless the caller tracks versions.
+ * PARITY UNPINNED like regk_jute_frames: restated from zookeeper.jute / MultiTransactionRecord, tested against an
+ * independent restatement (oracle/pyoracle.py), not against a server.
+ */
+#define REGK_ZK_CREATE  1u
+#define REGK_ZK_DELETE  2u
+#define REGK_ZK_SETDATA 5u
+
+typedef struct regk_jute_opts {
+    uint32_t op;                    /* REGK_ZK_* */
+    uint32_t flags;                 /* REGK_OUT_DEVICE */
+    int32_t xid_base;
+    uint32_t zk_flags;              /* create: CreateMode bits (1 = EPHEMERAL) */
+    int32_t version;                /* delete / setData: expected version, -1 = any */
+    uint32_t group;                 /* 0: single requests; g >= 1: multi transactions of g operations */
+} regk_jute_opts;
+
+int         regk_jute_requests(regk_ctx *ctx, const regk_jute_opts *opts, regk_frames *out);
+
+/*
  * ---- the reader side: decode paths and payloads back into records (README.md:462-480, :587-664) -----------------
  * Inverse of regk_register_batch / regk_service_records for audits of registry contents and round-trip checks:
  *   path    -> domain (labels reversed back, '/' -> '.'); for host nodes the last component is the instance name

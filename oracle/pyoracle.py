@@ -131,6 +131,42 @@ def jute_create_request(path: bytes, data: bytes, xid: int, flags: int = 1) -> b
     return struct.pack(">i", len(body)) + body
 
 
+def jute_body(op: int, path: bytes, data: bytes = b"", flags: int = 1, version: int = -1) -> bytes:
+    """The request record of one operation, without any header: CreateRequest (op 1), DeleteRequest{ustring path;
+    int version} (op 2), SetDataRequest{ustring path; buffer data; int version} (op 5).  PARITY UNPINNED, as above."""
+    import struct
+    body = struct.pack(">i", len(path)) + path
+    if op == 1:
+        body += struct.pack(">i", len(data)) + data + struct.pack(">ii", 1, 31)
+        body += struct.pack(">i", 5) + b"world" + struct.pack(">i", 6) + b"anyone" + struct.pack(">i", flags)
+    elif op == 2:
+        body += struct.pack(">i", version)
+    elif op == 5:
+        body += struct.pack(">i", len(data)) + data + struct.pack(">i", version)
+    else:
+        raise ValueError(op)
+    return body
+
+
+def jute_request(op: int, path: bytes, data: bytes, xid: int, flags: int = 1, version: int = -1) -> bytes:
+    """len | RequestHeader{xid, type = op} | request record."""
+    import struct
+    body = struct.pack(">ii", xid, op) + jute_body(op, path, data, flags, version)
+    return struct.pack(">i", len(body)) + body
+
+
+def jute_multi(op: int, ops: list, xid: int, flags: int = 1, version: int = -1) -> bytes:
+    """One multi transaction (OpCode.multi = 14): RequestHeader, then per operation MultiHeader{int type; boolean
+    done; int err} = {op, false, -1} and the request record, closed by MultiHeader{-1, true, -1}
+    (MultiTransactionRecord.serialize).  `ops` is a list of (path, data)."""
+    import struct
+    body = struct.pack(">ii", xid, 14)
+    for path, data in ops:
+        body += struct.pack(">i", op) + b"\x00" + struct.pack(">i", -1) + jute_body(op, path, data, flags, version)
+    body += struct.pack(">i", -1) + b"\x01" + struct.pack(">i", -1)
+    return struct.pack(">i", len(body)) + body
+
+
 # --------------------------------------------------------------------------------- reader side (§8f-4)
 def path_to_domain(path: str, host_node: bool):
     """(domain, instance name) - inverse of domain_to_path / host_node_path for paths this library writes."""

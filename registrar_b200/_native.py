@@ -89,6 +89,14 @@ class CFrames(C.Structure):          # regk_frames
                 ("frame_bytes", C.c_void_p), ("frame_off", C.c_void_p), ("kernel_ms", C.c_float)]
 
 
+class CJuteOpts(C.Structure):        # regk_jute_opts
+    _fields_ = [("op", C.c_uint32), ("flags", C.c_uint32), ("xid_base", C.c_int32), ("zk_flags", C.c_uint32),
+                ("version", C.c_int32), ("group", C.c_uint32)]
+
+
+ZK_CREATE, ZK_DELETE, ZK_SETDATA = 1, 2, 5
+
+
 class CDecodeIn(C.Structure):        # regk_decode_in
     _fields_ = [("n", C.c_uint64), ("flags", C.c_uint32), ("host_nodes", C.c_uint32),
                 ("path_total", C.c_uint64), ("json_total", C.c_uint64),
@@ -130,7 +138,7 @@ EXPORTS = ["regk_abi_version", "regk_create", "regk_destroy", "regk_last_error",
            "regk_host_free", "regk_dev_alloc", "regk_dev_free", "regk_memcpy_h2d", "regk_memcpy_d2h",
            "regk_sync", "regk_set_option", "regk_get_option", "regk_ipc_export", "regk_ipc_open", "regk_ipc_close",
            "regk_gather_push", "regk_parent_dirs", "regk_job_bind", "regk_service_records",
-           "regk_jute_frames", "regk_decode"]
+           "regk_jute_frames", "regk_jute_requests", "regk_decode"]
 
 _lib = None
 
@@ -179,6 +187,7 @@ def load_library():
     lib.regk_job_bind.argtypes = [vp, C.POINTER(CJob)]
     lib.regk_service_records.argtypes = [vp, C.POINTER(CServiceBatch), C.POINTER(CResult)]
     lib.regk_jute_frames.argtypes = [vp, u32, C.c_int32, u32, C.POINTER(CFrames)]
+    lib.regk_jute_requests.argtypes = [vp, C.POINTER(CJuteOpts), C.POINTER(CFrames)]
     lib.regk_decode.argtypes = [vp, C.POINTER(CDecodeIn), C.POINTER(CDecodeOut)]
     _lib = lib
     return lib
@@ -366,6 +375,20 @@ class Context:
         out = CFrames()
         self._check(self._lib.regk_jute_frames(self._h, FLAG_OUT_DEVICE if device else 0, int(xid_base), int(zk_flags),
                                                C.byref(out)))
+        if device:
+            return out
+        n = int(out.n)
+        return (_as_np(out.frame_bytes, int(out.total), np.uint8).copy(), _as_np(out.frame_off, n + 1, np.uint64).copy(),
+                float(out.kernel_ms))
+
+    def jute_requests(self, op: int = ZK_CREATE, xid_base: int = 1, zk_flags: int = 1, version: int = -1, group: int = 0,
+                      device: bool = False):
+        """regk_jute_requests: create / delete / setData requests of the batch finished last, one per record
+        (group=0) or as multi transactions of `group` operations.  Returns (frame_bytes, frame_off uint64[frames+1],
+        kernel_ms), or the raw CFrames with device=True."""
+        o = CJuteOpts(int(op), FLAG_OUT_DEVICE if device else 0, int(xid_base), int(zk_flags), int(version), int(group))
+        out = CFrames()
+        self._check(self._lib.regk_jute_requests(self._h, C.byref(o), C.byref(out)))
         if device:
             return out
         n = int(out.n)

@@ -539,6 +539,24 @@ static int issue_d2h(regk_ctx *ctx, regk_ctx::Slot &slot)
     return REGK_OK;
 }
 
+template <bool MULTI>
+static cudaError_t launch_jute(const JuteParams &p, size_t smem, int device, cudaStream_t s)
+{
+    static std::mutex mu;
+    static size_t high[64];
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > high[device & 63]) {
+            cudaError_t e = cudaFuncSetAttribute(regk_jute_kernel<MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess)
+                return e;
+            high[device & 63] = smem;
+        }
+    }
+    regk_jute_kernel<MULTI><<<(unsigned)((p.n + JUTE_TILE - 1) / JUTE_TILE), JUTE_THREADS, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
 extern "C" {
 
 int regk_abi_version(void)
@@ -1750,27 +1768,70 @@ int regk_service_records(regk_ctx *ctx, const regk_service_batch *b, regk_result
 
 int regk_jute_frames(regk_ctx *ctx, uint32_t flags, int32_t xid_base, uint32_t zk_flags, regk_frames *out)
 {
-    if (!ctx || !out)
-        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_jute_frames: NULL argument");
+    regk_jute_opts o{};
+    o.op = REGK_ZK_CREATE;
+    o.flags = flags;
+    o.xid_base = xid_base;
+    o.zk_flags = zk_flags;
+    return regk_jute_requests(ctx, &o, out);
+}
+
+int regk_jute_requests(regk_ctx *ctx, const regk_jute_opts *o, regk_frames *out)
+{
+    if (!ctx || !o || !out)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_jute_requests: NULL argument");
     memset(out, 0, sizeof *out);
+    if (o->op != REGK_ZK_CREATE && o->op != REGK_ZK_DELETE && o->op != REGK_ZK_SETDATA)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_jute_requests: op %u is not create (1), delete (2) or setData (5)", o->op);
+    if (o->group > 65536)
+        return fail(ctx, REGK_ERR_INVALID_ARG, "regk_jute_requests: at most 65536 operations per multi transaction");
+    const bool has_data = o->op != REGK_ZK_DELETE;
     if (ctx->pending)
-        return fail(ctx, REGK_ERR_STATE, "regk_jute_frames: batches are still in flight; finish them first");
-    if (!ctx->last_path_off || !ctx->last_json_off || ctx->last_n != ctx->last_json_n)
-        return fail(ctx, REGK_ERR_STATE, "regk_jute_frames: no finished batch with both a path and a payload stream on this context");
+        return fail(ctx, REGK_ERR_STATE, "regk_jute_requests: batches are still in flight; finish them first");
+    if (!ctx->last_path_off || (has_data && (!ctx->last_json_off || ctx->last_n != ctx->last_json_n)))
+        return fail(ctx, REGK_ERR_STATE, "regk_jute_requests: no finished batch with %s on this context",
+            has_data ? "both a path and a payload stream" : "a path stream");
     const uint64_t n = ctx->last_n;
+    const bool multi = o->group != 0;
+    const uint64_t g = multi ? o->group : 1, frames = (n + g - 1) / g;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const bool dev_out = flags & REGK_OUT_DEVICE;
-    out->n = n;
+    const bool dev_out = o->flags & REGK_OUT_DEVICE;
+    out->n = frames;
     out->flags = dev_out ? REGK_OUT_DEVICE : 0;
     /* totals of the two streams: the closing offsets on the device */
     unsigned long long tot[2] = {0, 0};
     CK(cudaMemcpyAsync(&tot[0], ctx->last_path_off + n, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&tot[1], ctx->last_json_off + n, 8, cudaMemcpyDeviceToHost, s));
+    if (has_data)
+        CK(cudaMemcpyAsync(&tot[1], ctx->last_json_off + n, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    const uint64_t total = tot[0] + tot[1] + (uint64_t)JUTE_FIXED * n;
+    JuteParams p{};
+    p.n = n;
+    p.op = o->op;
+    p.mid = has_data ? 4u : 0u;
+    p.group = (uint32_t)g;
+    p.multi = multi ? 1u : 0u;
+    /* what follows the data: create - acl vector [OPEN_ACL_UNSAFE] + flags; delete / setData - the expected version */
+    uint8_t tail[48] = {0};
+    if (o->op == REGK_ZK_CREATE) {
+        static const uint8_t acl[27] = {0, 0, 0, 1, 0, 0, 0, 31, 0, 0, 0, 5, 'w', 'o', 'r', 'l', 'd', 0, 0, 0, 6, 'a', 'n', 'y', 'o', 'n', 'e'};
+        memcpy(tail, acl, 27);
+        for (int k = 0; k < 4; k++)
+            tail[27 + k] = (uint8_t)(o->zk_flags >> (24 - 8 * k));
+        p.tail_len = 31;
+    } else {
+        for (int k = 0; k < 4; k++)
+            tail[k] = (uint8_t)((uint32_t)o->version >> (24 - 8 * k));
+        p.tail_len = 4;
+    }
+    static const uint8_t multi_end[9] = {0xFF, 0xFF, 0xFF, 0xFF, 1, 0xFF, 0xFF, 0xFF, 0xFF};   /* MultiHeader {type -1, done, err -1} */
+    memcpy(tail + p.tail_len, multi_end, 9);
+    memcpy(p.tail, tail, sizeof p.tail);
+    p.per_rec = (multi ? JUTE_MULTI_HEAD : 0u) + 4u + p.mid + p.tail_len;
+    const uint64_t total = tot[0] + tot[1] + (uint64_t)p.per_rec * n + (uint64_t)JUTE_FRAME_HEAD * frames +
+        (multi ? (uint64_t)JUTE_MULTI_HEAD * frames : 0);
     int rc;
-    if ((rc = ensure_dev(ctx, ctx->jute_bytes, total + 32)) || (rc = ensure_dev(ctx, ctx->jute_off, (n + 1) * 8)))
+    if ((rc = ensure_dev(ctx, ctx->jute_bytes, total + 32)) || (rc = ensure_dev(ctx, ctx->jute_off, (frames + 1) * 8)))
         return rc;
     if ((rc = ensure_dev(ctx, ctx->svc_work, 256)))
         return rc;
@@ -1779,45 +1840,33 @@ int regk_jute_frames(regk_ctx *ctx, uint32_t flags, int32_t xid_base, uint32_t z
         CK(cudaMemsetAsync(ctx->jute_off.p, 0, 8, s));
     cudaEvent_t e0 = ctx->slots[0].ev[0], e1 = ctx->slots[0].ev[1];
     if (n) {
-        JuteParams p{};
-        p.n = n;
         p.path_bytes = ctx->last_path_bytes;
         p.path_off = ctx->last_path_off;
-        p.json_bytes = ctx->last_json_bytes;
-        p.json_off = ctx->last_json_off;
+        p.json_bytes = has_data ? ctx->last_json_bytes : nullptr;
+        p.json_off = has_data ? ctx->last_json_off : nullptr;
         p.out_bytes = (uint8_t *)ctx->jute_bytes.p;
         p.out_off = (unsigned long long *)ctx->jute_off.p;
         p.out_capacity = total;
-        p.xid_base = xid_base;
-        p.zk_flags = zk_flags;
+        p.xid_base = o->xid_base;
         p.status = (DevStatus *)ctx->svc_work.p;
         /* staging budgets: 9/8 of a tile's mean share of each stream plus slack (tiles beyond it go byte-wise) */
         p.path_cap = (uint32_t)align16(std::min<uint64_t>(tot[0] * JUTE_TILE / n * 9 / 8 + 1024, 65520));
-        p.json_cap = (uint32_t)align16(std::min<uint64_t>(tot[1] * JUTE_TILE / n * 9 / 8 + 1024, 65520));  /* lengths travel as 16 bits */
+        p.json_cap = has_data ? (uint32_t)align16(std::min<uint64_t>(tot[1] * JUTE_TILE / n * 9 / 8 + 1024, 65520)) : 0u;  /* lengths travel as 16 bits */
         p.path_limit = tot[0] + 16;                 /* every stream buffer of this library has >= 16 bytes of slack */
-        p.json_limit = tot[1] + 16;
-        /* ... + one owner byte per 16-byte output block of a tile that fits the staging budgets */
-        const size_t owner_bytes = 3 * ((p.path_cap + p.json_cap + JUTE_FIXED * JUTE_TILE) / 16 + 32);   /* owner u8 + list u16 per block */
-        const size_t smem = 34 * 16 + 16 + JUTE_TILE * 20 + 16 + 32 + 16 + (size_t)p.path_cap + 16 + p.json_cap + 48 + owner_bytes;
-        static std::mutex mu;
-        static size_t high[64];
-        {
-            std::lock_guard<std::mutex> lock(mu);
-            if (smem > high[ctx->device & 63]) {
-                CK(cudaFuncSetAttribute(regk_jute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                high[ctx->device & 63] = smem;
-            }
-        }
+        p.json_limit = has_data ? tot[1] + 16 : 0;
+        /* ... + one owner byte and one list entry per 16-byte output block of a tile that fits the staging budgets */
+        const uint32_t max_fixed = p.per_rec + JUTE_FRAME_HEAD + JUTE_MULTI_HEAD;
+        const size_t owner_bytes = 3 * ((p.path_cap + p.json_cap + max_fixed * JUTE_TILE) / 16 + 32);   /* owner u8 + list u16 per block */
+        const size_t smem = 34 * 16 + 16 + JUTE_TILE * JUTE_SLOT + 16 + 48 + 16 + (size_t)p.path_cap + 16 + p.json_cap + 48 + owner_bytes;
         CK(cudaEventRecord(e0, s));
-        regk_jute_kernel<<<(unsigned)((n + JUTE_TILE - 1) / JUTE_TILE), JUTE_THREADS, smem, s>>>(p);
-        CK(cudaGetLastError());
+        CK(multi ? launch_jute<true>(p, smem, ctx->device, s) : launch_jute<false>(p, smem, ctx->device, s));
         CK(cudaEventRecord(e1, s));
         out->launches = 1;
     }
     CK(cudaMemcpyAsync(ctx->slots[0].h_status, ctx->svc_work.p, sizeof(DevStatus), cudaMemcpyDeviceToHost, s));
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess)
-        return fail(ctx, REGK_ERR_CUDA, "regk_jute_frames: kernel execution failed: %s", cudaGetErrorString(e));
+        return fail(ctx, REGK_ERR_CUDA, "regk_jute_requests: kernel execution failed: %s", cudaGetErrorString(e));
     if (ctx->slots[0].h_status->overflow)
         return fail(ctx, REGK_ERR_CUDA, "internal error: frame capacity bound exceeded");
     if (n)
@@ -1828,11 +1877,11 @@ int regk_jute_frames(regk_ctx *ctx, uint32_t flags, int32_t xid_base, uint32_t z
         out->frame_off = (const uint64_t *)ctx->jute_off.p;
         return REGK_OK;
     }
-    if ((rc = ensure_host(ctx, ctx->h_jute_bytes, total + 16)) || (rc = ensure_host(ctx, ctx->h_jute_off, (n + 1) * 8)))
+    if ((rc = ensure_host(ctx, ctx->h_jute_bytes, total + 16)) || (rc = ensure_host(ctx, ctx->h_jute_off, (frames + 1) * 8)))
         return rc;
     if (total)
         CK(cudaMemcpyAsync(ctx->h_jute_bytes.p, ctx->jute_bytes.p, total, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(ctx->h_jute_off.p, ctx->jute_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_jute_off.p, ctx->jute_off.p, (frames + 1) * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     out->frame_bytes = (const uint8_t *)ctx->h_jute_bytes.p;
     out->frame_off = (const uint64_t *)ctx->h_jute_off.p;

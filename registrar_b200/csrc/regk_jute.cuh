@@ -42,68 +42,80 @@ namespace regk {
 
 constexpr uint32_t JUTE_TILE = 64;              /* records per CTA */
 constexpr uint32_t JUTE_THREADS = 128;
-constexpr uint32_t JUTE_FIXED = 51;             /* framing bytes per record */
-constexpr uint32_t JUTE_HEAD = 16;              /* len, xid, type, path length */
-constexpr uint32_t JUTE_TAIL = 31;              /* acl count, perms, scheme, id, flags */
+constexpr uint32_t JUTE_SLOT = 32;              /* per-record framing slot in shared memory: the head RIGHT-aligned so that it
+                                                   ends at byte 28, the data length in bytes 28..31 */
+constexpr uint32_t JUTE_FRAME_HEAD = 12;        /* len, xid, type: once per frame */
+constexpr uint32_t JUTE_MULTI_HEAD = 9;         /* MultiHeader {int type; boolean done; int err}: in front of every operation */
+constexpr uint32_t JUTE_TAIL_MAX = 31;          /* create: acl count, perms, scheme, id, flags */
+enum : uint32_t { JUTE_OP_CREATE = 1, JUTE_OP_DELETE = 2, JUTE_OP_SETDATA = 5, JUTE_OP_MULTI = 14 };
 
 struct JuteParams {
     uint64_t n;
     const uint8_t *path_bytes;
     const unsigned long long *path_off;         /* [n+1] */
-    const uint8_t *json_bytes;
+    const uint8_t *json_bytes;                  /* NULL when the operation carries no data (delete) */
     const unsigned long long *json_off;         /* [n+1] */
     uint8_t *out_bytes;
-    unsigned long long *out_off;                /* [n+1] */
+    unsigned long long *out_off;                /* [frames+1] */
     uint64_t out_capacity;
     int32_t xid_base;
-    uint32_t zk_flags;
+    uint32_t op;                                /* JUTE_OP_CREATE / DELETE / SETDATA */
+    uint32_t mid;                               /* 4: a data buffer follows the path (its length word), 0: none */
+    uint32_t tail_len;                          /* bytes behind the data: create 31 (acl + flags), delete / setData 4 (version) */
+    uint32_t tail[12];                          /* those bytes, then the 9 bytes that close a multi transaction */
+    uint32_t group;                             /* operations per frame: 1 unless `multi` */
+    uint32_t multi;                             /* 1: frames are multi transactions of `group` operations */
+    uint32_t per_rec;                           /* framing bytes every record carries: (multi ? 9 : 0) + 4 + mid + tail_len */
     uint32_t path_cap, json_cap;                /* shared-memory budgets of the staged slices (bytes, multiples of 16) */
     uint64_t path_limit, json_limit;            /* bytes readable behind path_bytes / json_bytes (whole 16-byte blocks are fetched) */
     DevStatus *status;
 };
 
-/* acl count = 1, perms = 31, "world", "anyone" (the flags word follows) */
-__device__ __constant__ uint8_t regk_jute_acl[27] = {0, 0, 0, 1, 0, 0, 0, 31, 0, 0, 0, 5, 'w', 'o', 'r', 'l', 'd',
-                                                    0, 0, 0, 6, 'a', 'n', 'y', 'o', 'n', 'e'};
-
-__device__ __forceinline__ uint8_t be_byte(uint32_t v, uint32_t k)     /* byte k (0 = most significant) of v */
+/* framing bytes in front of record i (i <= n): every record's own, 12 per frame started, 9 per multi frame closed */
+__device__ __forceinline__ unsigned long long jute_fixed_before(const JuteParams &p, uint64_t i)
 {
-    return (uint8_t)(v >> (24u - 8u * k));
+    const uint64_t starts = (i + p.group - 1) / p.group;
+    const uint64_t ends = i == p.n ? starts : i / p.group;
+    return (unsigned long long)p.per_rec * i + JUTE_FRAME_HEAD * starts + (p.multi ? JUTE_MULTI_HEAD * ends : 0ull);
 }
 
-/* byte `k` (0 .. 50) of the framing of a record: 0..15 head, 16..19 data length, 20..50 tail */
-__device__ __forceinline__ uint8_t jute_fixed_byte(uint32_t k, uint32_t P, uint32_t J, uint32_t xid, uint32_t zk_flags)
+__device__ __forceinline__ unsigned long long jute_rec_off(const JuteParams &p, uint64_t i)
 {
-    if (k < 4u)
-        return be_byte(P + J + JUTE_FIXED - 4u, k);
-    if (k < 8u)
-        return be_byte(xid, k - 4u);
-    if (k < 12u)
-        return be_byte(1u, k - 8u);
-    if (k < 16u)
-        return be_byte(P, k - 12u);
-    if (k < 20u)
-        return be_byte(J, k - 16u);
-    if (k < 47u)
-        return regk_jute_acl[k - 20u];
-    return be_byte(zk_flags, k - 47u);
+    return p.path_off[i] + (p.mid ? p.json_off[i] : 0ull) + jute_fixed_before(p, i);
 }
 
-/* one record's frame, written by the 32 lanes of a warp through `put(offset in frame, byte)` */
-template <class Put>
-__device__ __forceinline__ void jute_frame(const JuteParams &p, uint64_t r, uint32_t lane, Put put)
+__device__ __forceinline__ uint32_t bswap32(uint32_t v)
 {
-    const unsigned long long p0 = p.path_off[r], j0 = p.json_off[r];
-    const uint32_t P = (uint32_t)(p.path_off[r + 1] - p0), J = (uint32_t)(p.json_off[r + 1] - j0);
-    const uint32_t xid = (uint32_t)p.xid_base + (uint32_t)r;
-    for (uint32_t k = lane; k < JUTE_FIXED; k += 32u) {
-        const uint32_t at = k < JUTE_HEAD ? k : k < 20u ? P + k : P + J + k;   /* head | data length | tail */
-        put(at, jute_fixed_byte(k, P, J, xid, p.zk_flags));
+    return __byte_perm(v, 0u, 0x0123);
+}
+
+/*
+ * The framing slot of one record (8 little-endian words = 32 bytes as they go on the wire):
+ *   single request   bytes 12..27  len | xid | op | path length                      28..31 data length
+ *   multi operation  bytes  3..27  len | xid | 14 | op | done = 0 | err = -1 | path length   (a record that does not
+ *                    open a frame uses bytes 15..27 only)
+ * `frame_len` is only read for a record that opens a frame.
+ */
+template <bool MULTI>
+__device__ __forceinline__ void jute_slot(const JuteParams &p, uint32_t xid, uint32_t frame_len, uint32_t P, uint32_t J,
+    uint32_t (&h)[8])
+{
+    if (!MULTI) {
+        h[0] = h[1] = h[2] = 0u;
+        h[3] = bswap32(frame_len);
+        h[4] = bswap32(xid);
+        h[5] = bswap32(p.op);
+    } else {
+        const uint32_t x0 = bswap32(frame_len), x1 = bswap32(xid), x2 = bswap32(JUTE_OP_MULTI), x3 = bswap32(p.op);
+        h[0] = x0 << 24;
+        h[1] = (x0 >> 8) | (x1 << 24);
+        h[2] = (x1 >> 8) | (x2 << 24);
+        h[3] = (x2 >> 8) | (x3 << 24);
+        h[4] = x3 >> 8;                                         /* byte 19: done = false */
+        h[5] = 0xFFFFFFFFu;                                     /* err = -1 */
     }
-    for (uint32_t i = lane; i < P; i += 32u)
-        put(JUTE_HEAD + i, p.path_bytes[p0 + i]);
-    for (uint32_t i = lane; i < J; i += 32u)
-        put(JUTE_HEAD + P + 4u + i, p.json_bytes[j0 + i]);
+    h[6] = bswap32(P);
+    h[7] = bswap32(J);
 }
 
 /* byte masks of a 16-byte block: JUTE_GE[d] = bytes at index >= d, JUTE_LT[e] = bytes at index < e (d, e in 0..16) */
@@ -117,36 +129,36 @@ __device__ __forceinline__ uint4 mask_ge(uint32_t d)
     return m;
 }
 
-__device__ __forceinline__ uint32_t bswap32(uint32_t v)
-{
-    return __byte_perm(v, 0u, 0x0123);
-}
-
+template <bool MULTI>
 __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_foff[JUTE_TILE + 1], s_poff[JUTE_TILE + 1], s_joff[JUTE_TILE + 1];
     __shared__ uint32_t s_nlist;
-    __shared__ uint4 s_rec[JUTE_TILE];                          /* {frame offset, path offset, payload offset, P | J << 16} */
-    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    __shared__ uint4 s_rec[JUTE_TILE];          /* {frame offset, path source | head bytes << 24, payload source | tail bytes << 24, P | J << 16} */
+    const uint32_t t = threadIdx.x;
     const uint64_t r0 = (uint64_t)blockIdx.x * JUTE_TILE;
     const uint32_t nrec = (uint32_t)min((uint64_t)JUTE_TILE, p.n - r0);
+    const uint32_t mid = p.mid, g = p.group;
     /* tile extents in the three streams (uniform loads) */
-    const unsigned long long P0 = p.path_off[r0], P1 = p.path_off[r0 + nrec], J0 = p.json_off[r0], J1 = p.json_off[r0 + nrec];
-    const unsigned long long f0 = P0 + J0 + (unsigned long long)JUTE_FIXED * r0;
-    const unsigned long long f1 = P1 + J1 + (unsigned long long)JUTE_FIXED * (r0 + nrec);
+    const unsigned long long P0 = p.path_off[r0], P1 = p.path_off[r0 + nrec];
+    const unsigned long long J0 = mid ? p.json_off[r0] : 0ull, J1 = mid ? p.json_off[r0 + nrec] : 0ull;
+    const unsigned long long x0 = jute_fixed_before(p, r0);
+    const unsigned long long f0 = P0 + J0 + x0, f1 = P1 + J1 + jute_fixed_before(p, r0 + nrec);
     const uint32_t total = (uint32_t)(f1 - f0);
     const bool room = f1 <= p.out_capacity;
+    const uint64_t q0 = r0 / g;                                 /* frames opened before the one r0 lies in */
+    const uint32_t m0 = (uint32_t)(r0 - q0 * g);                /* r0's position inside its frame */
     /* dynamic shared memory (byte space shared by every segment source, 16 bytes of slack around each region):
-       [mask tables 2 x 17 x 16][hdr: 20 bytes per record][trailer 32][path slice][payload slice] */
+       [mask tables 2 x 17 x 16][framing slots: 32 bytes per record][tail 48][path slice][payload slice] */
     uint4 *s_ge = reinterpret_cast<uint4 *>(smem);
     uint4 *s_lt = s_ge + 17;
     const uint32_t HDR = 34u * 16u + 16u;                       /* byte offset of the per-record framing */
-    const uint32_t TAIL = HDR + JUTE_TILE * 20u + 16u;
-    const uint32_t PATH = TAIL + 32u + 16u;
+    const uint32_t TAIL = HDR + JUTE_TILE * JUTE_SLOT + 16u;
+    const uint32_t PATH = TAIL + 48u + 16u;
     const uint32_t plead = (uint32_t)P0 & 15u, jlead = (uint32_t)J0 & 15u;
-    const uint32_t np = (plead + (uint32_t)(P1 - P0) + 15u) & ~15u, nj = (jlead + (uint32_t)(J1 - J0) + 15u) & ~15u;
+    const uint32_t np = (plead + (uint32_t)(P1 - P0) + 15u) & ~15u, nj = mid ? (jlead + (uint32_t)(J1 - J0) + 15u) & ~15u : 0u;
     const uint32_t JSON = PATH + p.path_cap + 16u;
     const bool fits = room && np <= p.path_cap && nj <= p.json_cap && (P0 & ~15ull) + np <= p.path_limit &&
         (J0 & ~15ull) + nj <= p.json_limit;
@@ -160,54 +172,78 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
                 bulk_g2s(smem + JSON, p.json_bytes + (J0 & ~15ull), nj, &s_bar);
         }
     }
+    /* this thread's record: where it sits in its frame, what framing it carries */
+    const uint32_t mt = m0 + t;                                 /* t <= 64: no overflow concerns */
+    const uint32_t fq = MULTI ? mt / g : t, fm = MULTI ? mt - fq * g : 0u;
+    const bool first = fm == 0u;
+    const bool last = !MULTI || fm == g - 1u || r0 + t + 1u == p.n;
+    unsigned long long fo = 0;
     if (t <= nrec) {
-        const unsigned long long po = p.path_off[r0 + t], jo = p.json_off[r0 + t];
-        const unsigned long long fo = po + jo + (unsigned long long)JUTE_FIXED * (r0 + t);
+        const unsigned long long po = p.path_off[r0 + t], jo = mid ? p.json_off[r0 + t] : 0ull;
+        /* frames opened / closed in front of this record, relative to r0's */
+        const uint32_t opened = MULTI ? (mt + g - 1u) / g - (m0 + g - 1u) / g : t;
+        const uint32_t closed = MULTI ? (r0 + t == p.n ? opened + ((m0 + g - 1u) / g) - m0 / g : fq - m0 / g) : 0u;
+        fo = po + jo + x0 + (unsigned long long)p.per_rec * t + JUTE_FRAME_HEAD * opened + JUTE_MULTI_HEAD * closed;
         s_poff[t] = (uint32_t)(po - P0);
         s_joff[t] = (uint32_t)(jo - J0);
         s_foff[t] = (uint32_t)(fo - f0);
-        if (t < nrec || r0 + nrec == p.n)
-            p.out_off[r0 + t] = fo;
+        if (first && (t < nrec || r0 + nrec == p.n))
+            p.out_off[MULTI ? q0 + fq : r0 + t] = fo;           /* the closing entry: r0 + t == n */
+        else if (MULTI && t == nrec && r0 + nrec == p.n)
+            p.out_off[q0 + fq + 1u] = fo;                       /* n is not a multiple of the group size */
     }
     if (t < 17) {
         s_ge[t] = mask_ge(t);
-        const uint4 g = mask_ge(t);
-        s_lt[t] = make_uint4(~g.x, ~g.y, ~g.z, ~g.w);
+        const uint4 gm = mask_ge(t);
+        s_lt[t] = make_uint4(~gm.x, ~gm.y, ~gm.z, ~gm.w);
     }
-    if (t >= 32 && t < 40) {                                     /* the trailer: 27 constant bytes + the flags word */
-        const uint32_t k = t - 32u;
-        uint32_t w = 0;
-        for (uint32_t b = 0; b < 4; b++) {
-            const uint32_t at = 4u * k + b;
-            const uint32_t byte = at < 27u ? regk_jute_acl[at] : at < 31u ? be_byte(p.zk_flags, at - 27u) : 0u;
-            w |= byte << (8u * b);
-        }
-        reinterpret_cast<uint32_t *>(smem + TAIL)[k] = w;
-    }
+    if (t >= 32 && t < 44)                                      /* the tail: constant bytes, then the multi close */
+        reinterpret_cast<uint32_t *>(smem + TAIL)[t - 32u] = p.tail[t - 32u];
     if (!room) {
         if (t == 0)
             atomicOr(&p.status->overflow, 1u);
         return;
     }
+    const uint32_t hb = (first ? JUTE_FRAME_HEAD : 0u) + (MULTI ? JUTE_MULTI_HEAD : 0u) + 4u;
+    const uint32_t tb = p.tail_len + (MULTI && last ? JUTE_MULTI_HEAD : 0u);
+    uint32_t h[8];
+    if (t < nrec) {
+        const uint32_t P = (uint32_t)(p.path_off[r0 + t + 1] - p.path_off[r0 + t]);
+        const uint32_t J = mid ? (uint32_t)(p.json_off[r0 + t + 1] - p.json_off[r0 + t]) : 0u;
+        uint32_t frame_len = P + J + hb + mid + tb - 4u;
+        if (MULTI && first) {
+            const uint64_t e = min(r0 + t + (uint64_t)g, p.n);
+            frame_len = (uint32_t)(jute_rec_off(p, e) - fo) - 4u;
+        }
+        jute_slot<MULTI>(p, (uint32_t)p.xid_base + (uint32_t)(MULTI ? q0 + fq : r0 + t), frame_len, P, J, h);
+    }
     if (!fits) {
-        /* byte-wise fallback: a warp per record, straight to global memory */
-        for (uint32_t i = warp; i < nrec; i += JUTE_THREADS / 32u) {
-            const uint64_t r = r0 + i;
-            uint8_t *g = p.out_bytes + (p.path_off[r] + p.json_off[r] + (unsigned long long)JUTE_FIXED * r);
-            jute_frame(p, r, lane, [g](uint32_t at, uint8_t b) { g[at] = b; });
+        /* byte-wise fallback: a thread per record, straight to global memory */
+        if (t < nrec) {
+            uint8_t *gp = p.out_bytes + fo;
+            const uint8_t *hbytes = reinterpret_cast<const uint8_t *>(h), *tbytes = reinterpret_cast<const uint8_t *>(p.tail);
+            const uint32_t P = bswap32(h[6]), J = bswap32(h[7]);
+            const uint8_t *ps = p.path_bytes + p.path_off[r0 + t], *js = mid ? p.json_bytes + p.json_off[r0 + t] : nullptr;
+            for (uint32_t k = 0; k < hb; k++)
+                *gp++ = hbytes[28u - hb + k];
+            for (uint32_t k = 0; k < P; k++)
+                *gp++ = ps[k];
+            for (uint32_t k = 0; k < mid; k++)
+                *gp++ = hbytes[28u + k];
+            for (uint32_t k = 0; k < J; k++)
+                *gp++ = js[k];
+            for (uint32_t k = 0; k < tb; k++)
+                *gp++ = tbytes[k];
         }
         return;
     }
-    __syncthreads();                                            /* offsets, masks, trailer, mbarrier init */
-    if (t < nrec) {                                             /* header words + data length, big endian */
-        const uint32_t P = s_poff[t + 1] - s_poff[t], J = s_joff[t + 1] - s_joff[t];
-        uint32_t *h = reinterpret_cast<uint32_t *>(smem + HDR) + 5u * t;
-        h[0] = bswap32(P + J + JUTE_FIXED - 4u);
-        h[1] = bswap32((uint32_t)p.xid_base + (uint32_t)(r0 + t));
-        h[2] = bswap32(1u);
-        h[3] = bswap32(P);
-        h[4] = bswap32(J);
-        s_rec[t] = make_uint4(s_foff[t], PATH + plead + s_poff[t], JSON + jlead + s_joff[t], P | (J << 16));
+    __syncthreads();                                            /* offsets, masks, tail, mbarrier init */
+    if (t < nrec) {
+        uint4 *slot = reinterpret_cast<uint4 *>(smem + HDR + JUTE_SLOT * t);
+        slot[0] = make_uint4(h[0], h[1], h[2], h[3]);
+        slot[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        s_rec[t] = make_uint4(s_foff[t], (PATH + plead + s_poff[t]) | (hb << 24), (JSON + jlead + s_joff[t]) | (tb << 24),
+            bswap32(h[6]) | (bswap32(h[7]) << 16));
     }
     const unsigned long long a0 = f0 & ~15ull;
     const uint32_t lead = (uint32_t)(f0 - a0);
@@ -237,13 +273,14 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
         const int32_t bstart = (int32_t)(16u * b) - (int32_t)lead;
         const uint32_t i = s_owner[b];
         const uint4 rc = s_rec[i];
-        const uint32_t fo = (uint32_t)bstart - rc.x;            /* meaningful when bstart >= 0 */
+        const uint32_t fo_b = (uint32_t)bstart - rc.x;          /* meaningful when bstart >= 0 */
         const uint32_t P = rc.w & 0xFFFFu, J = rc.w >> 16;
+        const uint32_t ph = rc.y >> 24;                         /* head bytes of record i */
         const bool whole = bstart >= 0 && (uint32_t)bstart + 16u <= total;
-        const bool in_path = fo >= JUTE_HEAD && fo + 16u <= JUTE_HEAD + P;
-        const bool in_data = fo >= JUTE_HEAD + P + 4u && fo + 16u <= JUTE_HEAD + P + 4u + J;
+        const bool in_path = fo_b >= ph && fo_b + 16u <= ph + P;
+        const bool in_data = fo_b >= ph + P + mid && fo_b + 16u <= ph + P + mid + J;
         if (whole && (in_path || in_data)) {
-            const uint32_t src = in_path ? rc.y + (fo - JUTE_HEAD) : rc.z + (fo - JUTE_HEAD - P - 4u);
+            const uint32_t src = in_path ? (rc.y & 0xFFFFFFu) + (fo_b - ph) : (rc.z & 0xFFFFFFu) + (fo_b - ph - P - mid);
             uint32_t v[4];
             load16(sw, src, v);
             stg_v4(p.out_bytes + a0 + 16ull * b, make_uint4(v[0], v[1], v[2], v[3]));
@@ -262,26 +299,27 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
         uint32_t acc[4] = {0u, 0u, 0u, 0u};
         while (pos < end) {
             const uint4 rc = s_rec[i];                          /* one 128-bit load per step */
-            const uint32_t fo = pos - rc.x;
+            const uint32_t fo_b = pos - rc.x;
             const uint32_t P = rc.w & 0xFFFFu, J = rc.w >> 16;
+            const uint32_t ph = rc.y >> 24, pt = rc.z >> 24;
             uint32_t src, seg_end;
-            if (fo < JUTE_HEAD) {
-                src = HDR + 20u * i + fo;
-                seg_end = JUTE_HEAD;
-            } else if (fo < JUTE_HEAD + P) {
-                src = rc.y + (fo - JUTE_HEAD);
-                seg_end = JUTE_HEAD + P;
-            } else if (fo < JUTE_HEAD + P + 4u) {
-                src = HDR + 20u * i + 16u + (fo - JUTE_HEAD - P);
-                seg_end = JUTE_HEAD + P + 4u;
-            } else if (fo < JUTE_HEAD + P + 4u + J) {
-                src = rc.z + (fo - JUTE_HEAD - P - 4u);
-                seg_end = JUTE_HEAD + P + 4u + J;
+            if (fo_b < ph) {
+                src = HDR + JUTE_SLOT * i + 28u - ph + fo_b;
+                seg_end = ph;
+            } else if (fo_b < ph + P) {
+                src = (rc.y & 0xFFFFFFu) + (fo_b - ph);
+                seg_end = ph + P;
+            } else if (fo_b < ph + P + mid) {
+                src = HDR + JUTE_SLOT * i + 28u + (fo_b - ph - P);
+                seg_end = ph + P + mid;
+            } else if (fo_b < ph + P + mid + J) {
+                src = (rc.z & 0xFFFFFFu) + (fo_b - ph - P - mid);
+                seg_end = ph + P + mid + J;
             } else {
-                src = TAIL + (fo - JUTE_HEAD - P - 4u - J);
-                seg_end = JUTE_FIXED + P + J;
+                src = TAIL + (fo_b - ph - P - mid - J);
+                seg_end = ph + P + mid + J + pt;
             }
-            const uint32_t n = min(seg_end - fo, end - pos);
+            const uint32_t n = min(seg_end - fo_b, end - pos);
             const uint32_t d = (uint32_t)((int32_t)pos - bstart);       /* destination byte inside the block */
             uint32_t v[4];
             load16(sw, src - d, v);                             /* source byte k lands on lane byte d + k */
@@ -291,16 +329,16 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
             acc[2] |= v[2] & mg.z & ml.z;
             acc[3] |= v[3] & mg.w & ml.w;
             pos += n;
-            if (fo + n == JUTE_FIXED + P + J)
+            if (fo_b + n == ph + P + mid + J + pt)
                 i++;
         }
-        uint8_t *g = p.out_bytes + a0 + 16ull * b;
+        uint8_t *gp = p.out_bytes + a0 + 16ull * b;
         if (bstart >= 0 && (uint32_t)bstart + 16u <= total) {
-            stg_v4(g, make_uint4(acc[0], acc[1], acc[2], acc[3]));
+            stg_v4(gp, make_uint4(acc[0], acc[1], acc[2], acc[3]));
         } else {                                                /* the tile's ragged first / last block: its own bytes only */
             const uint32_t d0 = bstart < 0 ? (uint32_t)(-bstart) : 0u, d1 = end - (uint32_t)max(bstart, 0) + d0;
             for (uint32_t k = d0; k < d1; k++)
-                g[k] = (uint8_t)(acc[k >> 2] >> (8u * (k & 3u)));
+                gp[k] = (uint8_t)(acc[k >> 2] >> (8u * (k & 3u)));
         }
     }
 }

@@ -24,6 +24,22 @@ def test_jute_restatement_against_a_hand_assembled_frame():
     assert struct.unpack(">i", f[:4])[0] == len(f) - 4
 
 
+def test_jute_restatements_of_the_other_requests():
+    path, data = b"/us/joyent/test/h", b'{"type":"host"}'
+    assert pyoracle.jute_request(1, path, data, 7, flags=1) == pyoracle.jute_create_request(path, data, 7, 1)
+    d = pyoracle.jute_request(2, path, b"", 9, version=-1)
+    assert d == b"\x00\x00\x00\x21" + b"\x00\x00\x00\x09" + b"\x00\x00\x00\x02" + b"\x00\x00\x00\x11" + path + b"\xff\xff\xff\xff"
+    s = pyoracle.jute_request(5, path, data, 3, version=4)
+    assert s == (b"\x00\x00\x00\x34" + b"\x00\x00\x00\x03" + b"\x00\x00\x00\x05" + b"\x00\x00\x00\x11" + path +
+                 b"\x00\x00\x00\x0f" + data + b"\x00\x00\x00\x04")
+    m = pyoracle.jute_multi(2, [(b"/a", b""), (b"/bc", b"")], xid=5)
+    assert m == (b"\x00\x00\x00\x38" + b"\x00\x00\x00\x05" + b"\x00\x00\x00\x0e" +     # 8 + (9 + 6 + 4) + (9 + 7 + 4) + 9
+                 b"\x00\x00\x00\x02" + b"\x00" + b"\xff\xff\xff\xff" + b"\x00\x00\x00\x02/a" + b"\xff\xff\xff\xff" +
+                 b"\x00\x00\x00\x02" + b"\x00" + b"\xff\xff\xff\xff" + b"\x00\x00\x00\x03/bc" + b"\xff\xff\xff\xff" +
+                 b"\xff\xff\xff\xff" + b"\x01" + b"\xff\xff\xff\xff")
+    assert struct.unpack(">i", m[:4])[0] == len(m) - 4
+
+
 def test_path_to_domain_restatement():
     assert pyoracle.path_to_domain("/us/joyent/emy-10/authcache/a2674d3b-a9c4-46bc-a835-b6ce21d522c2", True) == \
         ("authcache.emy-10.joyent.us", "a2674d3b-a9c4-46bc-a835-b6ce21d522c2")     # README.md:474-477
@@ -79,6 +95,61 @@ def test_gpu_jute_frames_edges(ctx):
     ctx.register_batch(RecordBatch.from_records(recs), payloads=False)
     with pytest.raises(RegkError):
         ctx.jute_frames()                                            # needs both streams
+
+
+def requests_of(res, op, xid_base, group, flags=1, version=-1):
+    """(bytes of all frames, frame offsets) as the restatement builds them."""
+    data = (lambda i: res.json(i)) if op != 2 else (lambda i: b"")
+    frames = []
+    if group == 0:
+        frames = [pyoracle.jute_request(op, res.path(i), data(i), xid_base + i, flags, version) for i in range(res.n)]
+    else:
+        for k, a in enumerate(range(0, res.n, group)):
+            ops = [(res.path(i), data(i)) for i in range(a, min(a + group, res.n))]
+            frames.append(pyoracle.jute_multi(op, ops, xid_base + k, flags, version))
+    off = np.concatenate([[0], np.cumsum([len(f) for f in frames])]).astype(np.uint64)
+    return b"".join(frames), off
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", [1, 2, 5])
+@pytest.mark.parametrize("group", [0, 1, 7, 64, 100, 5000])
+def test_gpu_jute_requests_and_transactions(ctx, op, group):
+    """create / delete / setData, one request per record and as multi transactions whose groups are smaller than,
+    equal to, larger than and not aligned with the kernel's 64-record tiles (and one group larger than the batch)."""
+    n = 3001
+    res = ctx.register_batch(synth.generate("config3", n=n, start=17))
+    fb, fo, ms = ctx.jute_requests(op=op, xid_base=40, zk_flags=1, version=-1 if op == 2 else 12, group=group)
+    want, woff = requests_of(res, op, 40, group, 1, -1 if op == 2 else 12)
+    assert np.array_equal(fo, woff)
+    assert bytes(fb) == want
+
+
+@pytest.mark.gpu
+def test_gpu_jute_requests_edges(ctx):
+    from registrar_b200._native import RegkError
+    recs = [{"domain": "a.b", "hostname": "h", "type": "host", "address": "1.2.3.4"}]
+    for n in (1, 2, 63, 64, 65, 128, 129):
+        res = ctx.register_batch(RecordBatch.from_records(recs * n))
+        for op, group in ((2, 0), (2, 3), (1, 64), (5, 2), (1, 1)):
+            fb, fo, _ = ctx.jute_requests(op=op, xid_base=-3, zk_flags=0, group=group)
+            want, woff = requests_of(res, op, -3, group, 0, -1)
+            assert np.array_equal(fo, woff) and bytes(fb) == want, (n, op, group)
+    # delete requests need no payload stream; the others do
+    res = ctx.register_batch(RecordBatch.from_records(recs * 70), payloads=False)
+    fb, fo, _ = ctx.jute_requests(op=2, group=16)
+    want, woff = requests_of(res, 2, 1, 16)
+    assert np.array_equal(fo, woff) and bytes(fb) == want
+    with pytest.raises(RegkError):
+        ctx.jute_requests(op=5)
+    with pytest.raises(RegkError):
+        ctx.jute_requests(op=3)
+    # tiles beyond the staging budget (byte-wise route), transactions across them
+    res = ctx.register_batch(synth.generate("config5", n=3000))
+    for op, group in ((1, 0), (1, 10), (2, 33)):
+        fb, fo, _ = ctx.jute_requests(op=op, xid_base=2, group=group)
+        want, woff = requests_of(res, op, 2, group)
+        assert np.array_equal(fo, woff) and bytes(fb) == want
 
 
 def slot(dom_bytes, off, i, ln):

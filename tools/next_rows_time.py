@@ -34,7 +34,14 @@ P, J = int(res.path_total), int(res.json_total)
 best = lambda f, k=4: min(f() for _ in range(k))
 # wire frames: read both streams + their offsets, write frames + offsets
 ms = best(lambda: ctx.jute_frames(1, 1, device=True).kernel_ms)
-row("regk_jute_kernel", ms, (P + J + 16 * n) + (P + J + 51 * n + 8 * n))
+row("regk_jute_kernel<single> create", ms, (P + J + 16 * n) + (P + J + 51 * n + 8 * n))
+# the unlink list (DeleteRequest per node path) and create transactions of 100 operations
+fr = ctx.jute_requests(op=_native.ZK_DELETE, device=True)
+ms = best(lambda: ctx.jute_requests(op=_native.ZK_DELETE, device=True).kernel_ms)
+row("regk_jute_kernel<single> delete", ms, (P + 8 * n) + int(fr.total) + 8 * n)
+fr = ctx.jute_requests(op=_native.ZK_CREATE, group=100, device=True)
+ms = best(lambda: ctx.jute_requests(op=_native.ZK_CREATE, group=100, device=True).kernel_ms)
+row("regk_jute_kernel<multi> create x100", ms, (P + J + 16 * n) + int(fr.total) + 8 * int(fr.n))
 # reader side: read both streams + offsets, write domains (slot layout), records (40 B) and ports
 C = _native.C
 def dec():
