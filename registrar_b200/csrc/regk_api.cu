@@ -539,7 +539,7 @@ static int issue_d2h(regk_ctx *ctx, regk_ctx::Slot &slot)
     return REGK_OK;
 }
 
-template <bool MULTI>
+template <bool MULTI, bool DATA>
 static cudaError_t launch_jute(const JuteParams &p, size_t smem, int device, cudaStream_t s)
 {
     static std::mutex mu;
@@ -547,13 +547,13 @@ static cudaError_t launch_jute(const JuteParams &p, size_t smem, int device, cud
     {
         std::lock_guard<std::mutex> lock(mu);
         if (smem > high[device & 63]) {
-            cudaError_t e = cudaFuncSetAttribute(regk_jute_kernel<MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(regk_jute_kernel<MULTI, DATA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess)
                 return e;
             high[device & 63] = smem;
         }
     }
-    regk_jute_kernel<MULTI><<<(unsigned)((p.n + JUTE_TILE - 1) / JUTE_TILE), JUTE_THREADS, smem, s>>>(p);
+    regk_jute_kernel<MULTI, DATA><<<(unsigned)((p.n + JUTE_TILE - 1) / JUTE_TILE), JUTE_THREADS, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -1859,7 +1859,8 @@ int regk_jute_requests(regk_ctx *ctx, const regk_jute_opts *o, regk_frames *out)
         const size_t owner_bytes = 3 * ((p.path_cap + p.json_cap + max_fixed * JUTE_TILE) / 16 + 32);   /* owner u8 + list u16 per block */
         const size_t smem = 34 * 16 + 16 + JUTE_TILE * JUTE_SLOT + 16 + 48 + 16 + (size_t)p.path_cap + 16 + p.json_cap + 48 + owner_bytes;
         CK(cudaEventRecord(e0, s));
-        CK(multi ? launch_jute<true>(p, smem, ctx->device, s) : launch_jute<false>(p, smem, ctx->device, s));
+        CK(multi ? (has_data ? launch_jute<true, true>(p, smem, ctx->device, s) : launch_jute<true, false>(p, smem, ctx->device, s))
+                 : (has_data ? launch_jute<false, true>(p, smem, ctx->device, s) : launch_jute<false, false>(p, smem, ctx->device, s)));
         CK(cudaEventRecord(e1, s));
         out->launches = 1;
     }
@@ -1983,7 +1984,9 @@ int regk_decode(regk_ctx *ctx, const regk_decode_in *in, regk_decode_out *out)
         const uint64_t slack = (in_dev && !last) ? 0 : 16;     /* a caller's own device buffers end where they end */
         p.path_limit = path_total + slack;
         p.json_limit = json_total + slack;
-        const size_t dsmem = 2 * ((size_t)p.path_cap + 32) + p.json_cap + 32 + DEC_TILE * sizeof(Decoded) + 16;
+        /* [path slice, later the result records][slash bitmap][payload slice, later the domain image] (regk_decode.cuh) */
+        const size_t dsmem = std::max<size_t>((size_t)p.path_cap + 32, DEC_TILE * sizeof(Decoded)) + ((p.path_cap / 8 + 47) & ~15u) +
+            std::max<size_t>(p.json_cap, p.path_cap) + 32 + 16;
         {
             static std::mutex mu;
             static size_t high[64];

@@ -14,12 +14,15 @@
  *                    vouch for it.  Checks the README states: the inner object's name equals the value of "type";
  *                    ttl and ports are integers.  Additionally: both "address" members agree (registrar always
  *                    writes the same string twice, lib/register.js:143,153).
- * One thread per record, byte-serial - but over SHARED memory: a CTA stages its 128 records' slices of both streams
- * with two cp.async.bulk copies, parses them there, composes the domains into a shared-memory image of the tile's
- * slot range and the 40-byte result records into a shared-memory table, and both leave coalesced (one bulk store +
- * ragged ends, word-wise copy).  The first version read and wrote global memory byte by byte from every thread:
- * 5.7 ms per 10 M records (0.08 of the HBM peak); numbers of this one in DESIGN.md §4.  Tiles whose slices exceed
- * the staging budget take the old route.
+ * One thread per record over SHARED memory: a CTA stages its 128 records' slices of both streams with two
+ * cp.async.bulk copies.  Paths: a cooperative pre-pass leaves a slash bitmap and turns every '/' into '.', then each
+ * thread walks its components from the last to the first with one clz per component and copies them in 16-byte
+ * register blocks into a shared-memory image of the tile's slot range (the encoder's label loop, run backwards;
+ * regk_decode_core.cuh decode_path2).  Payloads: a cursor-style recogniser on 4-byte windows (literals, string scans,
+ * comparisons word-wise).  The 40-byte result records go to a shared-memory table; image and table leave coalesced (one
+ * bulk store + ragged ends, word-wise copy).  History: every thread reading and writing global memory byte by byte
+ * 5.7 ms per 10 M records (0.08 of the HBM peak); byte-serial over shared memory 3.99 ms (0.12); this version:
+ * DESIGN.md §4.  Tiles whose slices exceed the staging budget take the byte-wise route over global memory.
  * Outputs: regk_decoded[n] (include/regk.h), the domains in SLOT layout (domain i at byte path_off[i] of a buffer as
  * large as the path stream: a domain is never longer than its path) and the ports in slot layout (record i's
  * ports at element json_off[i] / 2 of a uint32 buffer of json_total / 2 + 1 elements: a port takes at least two
@@ -59,7 +62,7 @@ __device__ __forceinline__ void decode_one(const DecodeParams &p, uint64_t r, co
     if (path)
         d.flags |= decode_path(path, pn, p.host_nodes != 0, dom, d);
     if (json)
-        d.flags |= decode_payload(json, jn, d, ports);
+        d.flags |= decode_payload<true>(json, jn, d, ports);      /* global memory, no slack guaranteed */
 }
 
 __global__ void __launch_bounds__(DEC_TILE) regk_decode_kernel(const DecodeParams p)
@@ -78,9 +81,15 @@ __global__ void __launch_bounds__(DEC_TILE) regk_decode_kernel(const DecodeParam
     const uint32_t np = (plead + (uint32_t)(P1 - P0) + 15u) & ~15u, nj = (jlead + (uint32_t)(J1 - J0) + 15u) & ~15u;
     const bool fits = p.path_cap + p.json_cap != 0 && P1 >= P0 && J1 >= J0 && P1 - P0 <= p.path_cap && J1 - J0 <= p.json_cap &&
         np <= p.path_cap + 16u && nj <= p.json_cap + 16u && (P0 & ~15ull) + np <= p.path_limit && (J0 & ~15ull) + nj <= p.json_limit;
-    /* [path slice][domain image, same 16-byte phase][payload slice][result records] */
-    uint8_t *s_path = smem, *s_dom = s_path + p.path_cap + 32u, *s_json = s_dom + p.path_cap + 32u;
-    Decoded *s_rec = reinterpret_cast<Decoded *>(s_json + p.json_cap + 32u);
+    /* Shared memory: [A: path slice][slash bitmap][B: payload slice].  Both regions are used twice: once the payloads are
+       parsed, B becomes the domain image (same 16-byte phase as the path slice); once the domains are composed, A becomes
+       the table of result records.  37 KB instead of 50 KB per CTA for config 3: 6 resident CTAs instead of 4. */
+    const uint32_t a_bytes = max(p.path_cap + 32u, DEC_TILE * (uint32_t)sizeof(Decoded));
+    const uint32_t b_bytes = max(p.json_cap, p.path_cap) + 32u;
+    uint8_t *s_path = smem, *s_bits = s_path + a_bytes, *s_json = s_bits + ((p.path_cap / 8u + 47u) & ~15u);
+    uint8_t *s_dom = s_json;
+    Decoded *s_rec = reinterpret_cast<Decoded *>(s_path);
+    (void)b_bytes;
     const unsigned long long pa = p.path_bytes ? p.path_off[r] : 0, pb = p.path_bytes ? p.path_off[r + 1] : 0;
     const unsigned long long ja = p.json_bytes ? p.json_off[r] : 0, jb = p.json_bytes ? p.json_off[r + 1] : 0;
     Decoded d;
@@ -100,14 +109,31 @@ __global__ void __launch_bounds__(DEC_TILE) regk_decode_kernel(const DecodeParam
         if (nj)
             bulk_g2s(s_json, p.json_bytes + (J0 & ~15ull), nj, &s_bar);
     }
-    for (uint32_t i = t; i < (np >> 4); i += DEC_TILE)          /* slot bytes no domain covers stay zero */
-        reinterpret_cast<uint4 *>(s_dom)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();                                            /* mbarrier init */
     mbar_wait(&s_bar, 0);
+    d.flags = 0;
+    d.dom_len = d.host_pos = d.host_len = d.type_pos = d.type_len = d.addr_pos = d.addr_len = 0;
+    d.ttl = INT32_MIN;
+    d.nports = 0xFFFFFFFFu;
+    if (p.path_bytes)   /* cooperative pre-pass: slash bitmap, '/' -> '.' (vectorised, no divergence) */
+        prepass_slashes(reinterpret_cast<uint32_t *>(s_path), reinterpret_cast<uint16_t *>(s_bits), np >> 4, t, DEC_TILE);
+    if (live && p.json_bytes)
+        d.flags |= decode_payload<false>(s_json + jlead + (uint32_t)(ja - J0), (uint32_t)(jb - ja), d, p.ports + (ja >> 1));
+    WordSink sink;
+    sink.init(reinterpret_cast<uint32_t *>(s_dom), plead + (uint32_t)(pa - P0));
+    if (p.path_bytes) {
+        __syncthreads();                                        /* payloads parsed (B is free), bitmap complete */
+        for (uint32_t i = t; i < (np >> 4); i += DEC_TILE)      /* slot bytes no domain covers stay zero */
+            reinterpret_cast<uint4 *>(s_dom)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        if (live)                                               /* phase A: whole words of the domain */
+            d.flags |= decode_path2(reinterpret_cast<const uint32_t *>(s_path), reinterpret_cast<const uint32_t *>(s_bits),
+                plead + (uint32_t)(pa - P0), (uint32_t)(pb - pa), p.host_nodes != 0, sink, d);
+    }
+    __syncthreads();                                            /* A is free */
     if (live) {
-        decode_one(p, r, p.path_bytes ? s_path + plead + (uint32_t)(pa - P0) : nullptr, (uint32_t)(pb - pa),
-            s_dom + plead + (uint32_t)(pa - P0), p.json_bytes ? s_json + jlead + (uint32_t)(ja - J0) : nullptr,
-            (uint32_t)(jb - ja), p.ports + (ja >> 1), d);
+        if (p.path_bytes)
+            sink.tail();                                        /* phase B: the words neighbours share */
         s_rec[t] = d;
     }
     fence_proxy_async();

@@ -71,19 +71,6 @@ struct JuteParams {
     DevStatus *status;
 };
 
-/* framing bytes in front of record i (i <= n): every record's own, 12 per frame started, 9 per multi frame closed */
-__device__ __forceinline__ unsigned long long jute_fixed_before(const JuteParams &p, uint64_t i)
-{
-    const uint64_t starts = (i + p.group - 1) / p.group;
-    const uint64_t ends = i == p.n ? starts : i / p.group;
-    return (unsigned long long)p.per_rec * i + JUTE_FRAME_HEAD * starts + (p.multi ? JUTE_MULTI_HEAD * ends : 0ull);
-}
-
-__device__ __forceinline__ unsigned long long jute_rec_off(const JuteParams &p, uint64_t i)
-{
-    return p.path_off[i] + (p.mid ? p.json_off[i] : 0ull) + jute_fixed_before(p, i);
-}
-
 __device__ __forceinline__ uint32_t bswap32(uint32_t v)
 {
     return __byte_perm(v, 0u, 0x0123);
@@ -129,7 +116,7 @@ __device__ __forceinline__ uint4 mask_ge(uint32_t d)
     return m;
 }
 
-template <bool MULTI>
+template <bool MULTI, bool DATA>
 __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -140,16 +127,24 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
     const uint32_t t = threadIdx.x;
     const uint64_t r0 = (uint64_t)blockIdx.x * JUTE_TILE;
     const uint32_t nrec = (uint32_t)min((uint64_t)JUTE_TILE, p.n - r0);
-    const uint32_t mid = p.mid, g = p.group;
+    const uint32_t mid = DATA ? 4u : 0u, g = MULTI ? p.group : 1u;
     /* tile extents in the three streams (uniform loads) */
     const unsigned long long P0 = p.path_off[r0], P1 = p.path_off[r0 + nrec];
-    const unsigned long long J0 = mid ? p.json_off[r0] : 0ull, J1 = mid ? p.json_off[r0 + nrec] : 0ull;
-    const unsigned long long x0 = jute_fixed_before(p, r0);
-    const unsigned long long f0 = P0 + J0 + x0, f1 = P1 + J1 + jute_fixed_before(p, r0 + nrec);
+    const unsigned long long J0 = DATA ? p.json_off[r0] : 0ull, J1 = DATA ? p.json_off[r0 + nrec] : 0ull;
+    const uint64_t q0 = MULTI ? r0 / g : r0;                    /* frames opened before the one r0 lies in */
+    const uint32_t m0 = (uint32_t)(r0 - q0 * g);                /* r0's position inside its frame */
+    /* framing bytes in front of record r0 + d (d <= 64; r0 + d <= n): every record's own, 12 per frame opened, 9 per
+       multi frame closed */
+    auto fixed_before = [&](uint32_t d) -> unsigned long long {
+        if (!MULTI)
+            return (unsigned long long)(p.per_rec + JUTE_FRAME_HEAD) * (r0 + d);
+        const uint32_t md = m0 + d, fl = md / g, ce = (md + g - 1u) / g;
+        return (unsigned long long)p.per_rec * (r0 + d) + (unsigned long long)JUTE_FRAME_HEAD * (q0 + ce) +
+            (unsigned long long)JUTE_MULTI_HEAD * (q0 + (r0 + d == p.n ? ce : fl));
+    };
+    const unsigned long long f0 = P0 + J0 + fixed_before(0), f1 = P1 + J1 + fixed_before(nrec);
     const uint32_t total = (uint32_t)(f1 - f0);
     const bool room = f1 <= p.out_capacity;
-    const uint64_t q0 = r0 / g;                                 /* frames opened before the one r0 lies in */
-    const uint32_t m0 = (uint32_t)(r0 - q0 * g);                /* r0's position inside its frame */
     /* dynamic shared memory (byte space shared by every segment source, 16 bytes of slack around each region):
        [mask tables 2 x 17 x 16][framing slots: 32 bytes per record][tail 48][path slice][payload slice] */
     uint4 *s_ge = reinterpret_cast<uint4 *>(smem);
@@ -158,10 +153,10 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
     const uint32_t TAIL = HDR + JUTE_TILE * JUTE_SLOT + 16u;
     const uint32_t PATH = TAIL + 48u + 16u;
     const uint32_t plead = (uint32_t)P0 & 15u, jlead = (uint32_t)J0 & 15u;
-    const uint32_t np = (plead + (uint32_t)(P1 - P0) + 15u) & ~15u, nj = mid ? (jlead + (uint32_t)(J1 - J0) + 15u) & ~15u : 0u;
+    const uint32_t np = (plead + (uint32_t)(P1 - P0) + 15u) & ~15u, nj = DATA ? (jlead + (uint32_t)(J1 - J0) + 15u) & ~15u : 0u;
     const uint32_t JSON = PATH + p.path_cap + 16u;
-    const bool fits = room && np <= p.path_cap && nj <= p.json_cap && (P0 & ~15ull) + np <= p.path_limit &&
-        (J0 & ~15ull) + nj <= p.json_limit;
+    const bool fits = room && np <= p.path_cap && (P0 & ~15ull) + np <= p.path_limit &&
+        (!DATA || (nj <= p.json_cap && (J0 & ~15ull) + nj <= p.json_limit));
     if (t == 0) {
         mbar_init(&s_bar, 1);
         if (fits) {
@@ -179,11 +174,8 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
     const bool last = !MULTI || fm == g - 1u || r0 + t + 1u == p.n;
     unsigned long long fo = 0;
     if (t <= nrec) {
-        const unsigned long long po = p.path_off[r0 + t], jo = mid ? p.json_off[r0 + t] : 0ull;
-        /* frames opened / closed in front of this record, relative to r0's */
-        const uint32_t opened = MULTI ? (mt + g - 1u) / g - (m0 + g - 1u) / g : t;
-        const uint32_t closed = MULTI ? (r0 + t == p.n ? opened + ((m0 + g - 1u) / g) - m0 / g : fq - m0 / g) : 0u;
-        fo = po + jo + x0 + (unsigned long long)p.per_rec * t + JUTE_FRAME_HEAD * opened + JUTE_MULTI_HEAD * closed;
+        const unsigned long long po = p.path_off[r0 + t], jo = DATA ? p.json_off[r0 + t] : 0ull;
+        fo = po + jo + fixed_before(t);
         s_poff[t] = (uint32_t)(po - P0);
         s_joff[t] = (uint32_t)(jo - J0);
         s_foff[t] = (uint32_t)(fo - f0);
@@ -206,32 +198,39 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
     }
     const uint32_t hb = (first ? JUTE_FRAME_HEAD : 0u) + (MULTI ? JUTE_MULTI_HEAD : 0u) + 4u;
     const uint32_t tb = p.tail_len + (MULTI && last ? JUTE_MULTI_HEAD : 0u);
-    uint32_t h[8];
-    if (t < nrec) {
+    /* the record's framing slot: lengths, xid, and - for the record that opens a multi frame - the frame's length,
+       the distance to the record that opens the next one */
+    auto make_slot = [&](uint32_t (&h)[8]) {
         const uint32_t P = (uint32_t)(p.path_off[r0 + t + 1] - p.path_off[r0 + t]);
-        const uint32_t J = mid ? (uint32_t)(p.json_off[r0 + t + 1] - p.json_off[r0 + t]) : 0u;
+        const uint32_t J = DATA ? (uint32_t)(p.json_off[r0 + t + 1] - p.json_off[r0 + t]) : 0u;
         uint32_t frame_len = P + J + hb + mid + tb - 4u;
-        if (MULTI && first) {
-            const uint64_t e = min(r0 + t + (uint64_t)g, p.n);
-            frame_len = (uint32_t)(jute_rec_off(p, e) - fo) - 4u;
+        if (MULTI && first) {                                   /* the whole transaction: its operations, head and close */
+            const uint64_t i = r0 + t, e = min(i + (uint64_t)g, p.n);
+            frame_len = (uint32_t)(p.path_off[e] - p.path_off[i]) + (DATA ? (uint32_t)(p.json_off[e] - p.json_off[i]) : 0u) +
+                p.per_rec * (uint32_t)(e - i) + JUTE_FRAME_HEAD + JUTE_MULTI_HEAD - 4u;
         }
         jute_slot<MULTI>(p, (uint32_t)p.xid_base + (uint32_t)(MULTI ? q0 + fq : r0 + t), frame_len, P, J, h);
-    }
+    };
     if (!fits) {
         /* byte-wise fallback: a thread per record, straight to global memory */
         if (t < nrec) {
+            uint32_t h[8];
+            make_slot(h);
             uint8_t *gp = p.out_bytes + fo;
             const uint8_t *hbytes = reinterpret_cast<const uint8_t *>(h), *tbytes = reinterpret_cast<const uint8_t *>(p.tail);
             const uint32_t P = bswap32(h[6]), J = bswap32(h[7]);
-            const uint8_t *ps = p.path_bytes + p.path_off[r0 + t], *js = mid ? p.json_bytes + p.json_off[r0 + t] : nullptr;
+            const uint8_t *ps = p.path_bytes + p.path_off[r0 + t];
             for (uint32_t k = 0; k < hb; k++)
                 *gp++ = hbytes[28u - hb + k];
             for (uint32_t k = 0; k < P; k++)
                 *gp++ = ps[k];
-            for (uint32_t k = 0; k < mid; k++)
-                *gp++ = hbytes[28u + k];
-            for (uint32_t k = 0; k < J; k++)
-                *gp++ = js[k];
+            if (DATA) {
+                const uint8_t *js = p.json_bytes + p.json_off[r0 + t];
+                for (uint32_t k = 0; k < 4u; k++)
+                    *gp++ = hbytes[28u + k];
+                for (uint32_t k = 0; k < J; k++)
+                    *gp++ = js[k];
+            }
             for (uint32_t k = 0; k < tb; k++)
                 *gp++ = tbytes[k];
         }
@@ -239,11 +238,13 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
     }
     __syncthreads();                                            /* offsets, masks, tail, mbarrier init */
     if (t < nrec) {
+        uint32_t h[8];
+        make_slot(h);
         uint4 *slot = reinterpret_cast<uint4 *>(smem + HDR + JUTE_SLOT * t);
         slot[0] = make_uint4(h[0], h[1], h[2], h[3]);
         slot[1] = make_uint4(h[4], h[5], h[6], h[7]);
-        s_rec[t] = make_uint4(s_foff[t], (PATH + plead + s_poff[t]) | (hb << 24), (JSON + jlead + s_joff[t]) | (tb << 24),
-            bswap32(h[6]) | (bswap32(h[7]) << 16));
+        s_rec[t] = make_uint4(s_foff[t], (PATH + plead + s_poff[t]) | (MULTI ? hb << 24 : 0u),
+            (JSON + jlead + s_joff[t]) | (MULTI ? tb << 24 : 0u), bswap32(h[6]) | (bswap32(h[7]) << 16));
     }
     const unsigned long long a0 = f0 & ~15ull;
     const uint32_t lead = (uint32_t)(f0 - a0);
@@ -275,12 +276,13 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
         const uint4 rc = s_rec[i];
         const uint32_t fo_b = (uint32_t)bstart - rc.x;          /* meaningful when bstart >= 0 */
         const uint32_t P = rc.w & 0xFFFFu, J = rc.w >> 16;
-        const uint32_t ph = rc.y >> 24;                         /* head bytes of record i */
+        const uint32_t ph = MULTI ? rc.y >> 24 : JUTE_FRAME_HEAD + 4u;         /* head bytes of record i */
         const bool whole = bstart >= 0 && (uint32_t)bstart + 16u <= total;
         const bool in_path = fo_b >= ph && fo_b + 16u <= ph + P;
         const bool in_data = fo_b >= ph + P + mid && fo_b + 16u <= ph + P + mid + J;
         if (whole && (in_path || in_data)) {
-            const uint32_t src = in_path ? (rc.y & 0xFFFFFFu) + (fo_b - ph) : (rc.z & 0xFFFFFFu) + (fo_b - ph - P - mid);
+            const uint32_t ys = MULTI ? rc.y & 0xFFFFFFu : rc.y, zs = MULTI ? rc.z & 0xFFFFFFu : rc.z;
+            const uint32_t src = in_path ? ys + (fo_b - ph) : zs + (fo_b - ph - P - mid);
             uint32_t v[4];
             load16(sw, src, v);
             stg_v4(p.out_bytes + a0 + 16ull * b, make_uint4(v[0], v[1], v[2], v[3]));
@@ -301,19 +303,20 @@ __global__ void __launch_bounds__(JUTE_THREADS) regk_jute_kernel(const JuteParam
             const uint4 rc = s_rec[i];                          /* one 128-bit load per step */
             const uint32_t fo_b = pos - rc.x;
             const uint32_t P = rc.w & 0xFFFFu, J = rc.w >> 16;
-            const uint32_t ph = rc.y >> 24, pt = rc.z >> 24;
+            const uint32_t ph = MULTI ? rc.y >> 24 : JUTE_FRAME_HEAD + 4u, pt = MULTI ? rc.z >> 24 : p.tail_len;
+            const uint32_t ys = MULTI ? rc.y & 0xFFFFFFu : rc.y, zs = MULTI ? rc.z & 0xFFFFFFu : rc.z;
             uint32_t src, seg_end;
             if (fo_b < ph) {
                 src = HDR + JUTE_SLOT * i + 28u - ph + fo_b;
                 seg_end = ph;
             } else if (fo_b < ph + P) {
-                src = (rc.y & 0xFFFFFFu) + (fo_b - ph);
+                src = ys + (fo_b - ph);
                 seg_end = ph + P;
             } else if (fo_b < ph + P + mid) {
                 src = HDR + JUTE_SLOT * i + 28u + (fo_b - ph - P);
                 seg_end = ph + P + mid;
             } else if (fo_b < ph + P + mid + J) {
-                src = (rc.z & 0xFFFFFFu) + (fo_b - ph - P - mid);
+                src = zs + (fo_b - ph - P - mid);
                 seg_end = ph + P + mid + J;
             } else {
                 src = TAIL + (fo_b - ph - P - mid - J);

@@ -376,24 +376,56 @@ extern "C" uint64_t emul_services(uint64_t n, const uint8_t *srvce_bytes, const 
     return 0;
 }
 
-/* the reader side's per-record logic (regk_decode_core.cuh) on the host: out = n records of 10 uint32 words, domains in
-   slot layout (domain i at path_off[i]), ports in slot layout (element json_off[i] / 2) */
+/* the reader side (regk_decode_core.cuh) on the host, tile by tile as regk_decode_kernel runs it: out = n records of 10
+   uint32 words, domains in slot layout (domain i at path_off[i]), ports in slot layout (element json_off[i] / 2).
+   mode bit 0: host nodes; bit 1: the byte-wise route (global-memory fallback, guarded cursor) instead of the staged one */
 extern "C" void emul_decode(uint64_t n, const uint8_t *path_bytes, const uint64_t *path_off, const uint8_t *json_bytes,
-    const uint64_t *json_off, int host_nodes, uint32_t *out, uint8_t *dom_bytes, uint32_t *ports)
+    const uint64_t *json_off, int mode, uint32_t *out, uint8_t *dom_bytes, uint32_t *ports)
 {
-    for (uint64_t r = 0; r < n; r++) {
-        Decoded d;
-        d.flags = 0;
-        d.dom_len = d.host_pos = d.host_len = d.type_pos = d.type_len = d.addr_pos = d.addr_len = 0;
-        d.ttl = INT32_MIN;
-        d.nports = 0xFFFFFFFFu;
-        if (path_bytes)
-            d.flags |= decode_path(path_bytes + path_off[r], (uint32_t)(path_off[r + 1] - path_off[r]), host_nodes != 0,
-                dom_bytes + path_off[r], d);
-        if (json_bytes)
-            d.flags |= decode_payload(json_bytes + json_off[r], (uint32_t)(json_off[r + 1] - json_off[r]), d,
-                ports + (json_off[r] >> 1));
-        memcpy(out + 10 * r, &d, sizeof d);
+    const bool host_nodes = mode & 1, bytewise = mode & 2;
+    for (uint64_t r0 = 0; r0 < n; r0 += TILE) {
+        const uint32_t nrec = (uint32_t)std::min<uint64_t>(TILE, n - r0);
+        std::vector<Decoded> rec(nrec);
+        for (auto &d : rec) {
+            d.flags = 0;
+            d.dom_len = d.host_pos = d.host_len = d.type_pos = d.type_len = d.addr_pos = d.addr_len = 0;
+            d.ttl = INT32_MIN;
+            d.nports = 0xFFFFFFFFu;
+        }
+        if (path_bytes && bytewise) {
+            for (uint32_t t = 0; t < nrec; t++) {
+                const uint64_t r = r0 + t;
+                rec[t].flags |= decode_path(path_bytes + path_off[r], (uint32_t)(path_off[r + 1] - path_off[r]), host_nodes,
+                    dom_bytes + path_off[r], rec[t]);
+            }
+        } else if (path_bytes) {
+            const uint64_t P0 = path_off[r0], P1 = path_off[r0 + nrec];
+            const uint32_t lead = (uint32_t)(P0 & 15u), np = (lead + (uint32_t)(P1 - P0) + 15u) & ~15u;
+            std::vector<uint32_t> spath(np / 4 + 16, 0xA5A5A5A5u), sbits(np / 32 + 8, 0x3C3C3C3Cu), sdom(np / 4 + 16, 0u);
+            memcpy((uint8_t *)spath.data() + lead, path_bytes + P0, (size_t)(P1 - P0));
+            for (uint32_t tt = 0; tt < TILE; tt++)                   /* "threads" in a scrambled order */
+                prepass_slashes(spath.data(), (uint16_t *)sbits.data(), np >> 4, (tt * 37u) % TILE, TILE);
+            std::vector<WordSink> sinks(nrec);
+            for (uint32_t t = nrec; t-- > 0;) {                      /* phase A in reverse order: neighbours must not clobber */
+                const uint64_t r = r0 + t;
+                const uint32_t off = lead + (uint32_t)(path_off[r] - P0);
+                sinks[t].init(sdom.data(), off);
+                rec[t].flags |= decode_path2(spath.data(), sbits.data(), off, (uint32_t)(path_off[r + 1] - path_off[r]), host_nodes,
+                    sinks[t], rec[t]);
+            }
+            for (uint32_t t = 0; t < nrec; t++)                      /* phase B after the "barrier" */
+                sinks[t].tail();
+            memcpy(dom_bytes + P0, (const uint8_t *)sdom.data() + lead, (size_t)(P1 - P0));
+        }
+        for (uint32_t t = 0; t < nrec; t++) {
+            const uint64_t r = r0 + t;
+            if (json_bytes) {
+                const uint8_t *j = json_bytes + json_off[r];
+                const uint32_t jn = (uint32_t)(json_off[r + 1] - json_off[r]);
+                rec[t].flags |= bytewise ? decode_payload<true>(j, jn, rec[t], ports + (json_off[r] >> 1))
+                                         : decode_payload<false>(j, jn, rec[t], ports + (json_off[r] >> 1));
+            }
+            memcpy(out + 10 * r, &rec[t], sizeof(Decoded));
+        }
     }
 }
-

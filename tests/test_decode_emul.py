@@ -64,7 +64,7 @@ def expect(payload: bytes):
     return {"kind": flags, "type": t, "addr": a, "ttl": None if ttl is None else int(ttl), "ports": plist}
 
 
-def run(emul, payloads, paths=None, host_nodes=True):
+def run(emul, payloads, paths=None, host_nodes=True, bytewise=False):
     def streams(items):
         off = np.zeros(len(items) + 1, np.uint64)
         off[1:] = np.cumsum([len(x) for x in items])
@@ -76,7 +76,8 @@ def run(emul, payloads, paths=None, host_nodes=True):
     pb, po = streams(paths) if paths is not None else (None, None)
     dom = np.zeros((int(po[-1]) if po is not None else 0) + 16, np.uint8)
     ports = np.zeros((int(jo[-1]) if jo is not None else 0) // 2 + 16, np.uint32)
-    emul.emul_decode(C.c_uint64(n), vp(pb), vp(po), vp(jb), vp(jo), C.c_int(1 if host_nodes else 0), vp(out), vp(dom), vp(ports))
+    mode = (1 if host_nodes else 0) | (2 if bytewise else 0)    # bit 1: the byte-wise route (global-memory fallback)
+    emul.emul_decode(C.c_uint64(n), vp(pb), vp(po), vp(jb), vp(jo), C.c_int(mode), vp(out), vp(dom), vp(ports))
     return out.view(DECODED_DTYPE), dom, ports, po, jo
 
 
@@ -135,28 +136,79 @@ def test_encoder_output_is_recognised_and_mutations_are_not(emul):
              b'{"type":"service","service":{"type":"service","service":{"srvce":"a","srvce":"b","proto":"c","port":1}}}',
              b'{"type":"service","service":{"type":"service","service":{"srvce":"a","proto":"c","port":1,}}}']
     items = base + mutated + extra
-    rec, _, ports, _, jo = run(emul, items)
-    seen_valid = seen_invalid = 0
-    for i, p in enumerate(items):
-        check(rec, ports, jo, i, p)
-        if expect(p) is None:
-            seen_invalid += 1
-        else:
-            seen_valid += 1
-    assert seen_valid > len(base) and seen_invalid > len(base)      # the mutations hit both sides of the line
+    for bytewise in (False, True):                                  # the staged route's cursor and the guarded one
+        rec, _, ports, _, jo = run(emul, items, bytewise=bytewise)
+        seen_valid = seen_invalid = 0
+        for i, p in enumerate(items):
+            check(rec, ports, jo, i, p)
+            if expect(p) is None:
+                seen_invalid += 1
+            else:
+                seen_valid += 1
+        assert seen_valid > len(base) and seen_invalid > len(base)  # the mutations hit both sides of the line
 
 
-def test_paths_invert_on_the_host(emul):
+@pytest.mark.parametrize("bytewise", [False, True])
+def test_paths_invert_on_the_host(emul, bytewise):
     doms = ["a..b", "a.", ".a", "", "x", "1.moray.us-east.joyent.com", "..", "a.b.c.d.e.f.g", "A.B".lower()]
     paths = [pyoracle.domain_to_path(d).encode() for d in doms]
-    rec, dom, _, po, _ = run(emul, None, paths, host_nodes=False)
+    rec, dom, _, po, _ = run(emul, None, paths, host_nodes=False, bytewise=bytewise)
     assert [bytes(dom[int(po[i]):int(po[i]) + int(rec["dom_len"][i])]).decode() for i in range(len(doms))] == doms
     batch = synth.generate("config5", n=500)
     res = oracle.register_batch(batch)
     hp = [res.path(i) for i in range(res.n)]
-    rec, dom, _, po, _ = run(emul, None, hp, host_nodes=True)
+    rec, dom, _, po, _ = run(emul, None, hp, host_nodes=True, bytewise=bytewise)
     for i in range(res.n):
         r = batch.record(i)
         assert rec["flags"][i] == DEC_PATH_OK
         assert bytes(dom[int(po[i]):int(po[i]) + int(rec["dom_len"][i])]) == r["domain"].lower()
         assert hp[i][int(rec["host_pos"][i]):] == r["hostname"]
+
+
+def path_expect(path: bytes, host_nodes: bool):
+    """What the reader must report for ANY byte string: (ok, domain, host_pos, host_len) - the definition in prose
+    (README.md:462-480 read backwards): starts with '/'; for host nodes the part behind the last '/' is the instance name
+    and must not be empty; the components in front of it, reversed, joined by '.'."""
+    if not path.startswith(b"/"):
+        return False, b"", 0, 0
+    body = path
+    host_pos = host_len = 0
+    if host_nodes:
+        q = path.rfind(b"/") + 1
+        host_pos, host_len = q, len(path) - q
+        if host_len == 0:
+            return False, b"", host_pos, 0
+        body = path[:q - 1] if q > 1 else b"/"
+    comps = body[1:].split(b"/") if len(body) > 1 else []
+    return True, b".".join(reversed(comps)), host_pos, host_len
+
+
+@pytest.mark.parametrize("host_nodes", [False, True])
+def test_random_byte_strings_as_paths_both_routes_agree_with_the_definition(emul, host_nodes):
+    """Arbitrary bytes (slashes dense and sparse, bytes >= 0x80, empty strings, components longer than a 64-bit bitmap
+    window, records straddling the 128-record tiles at every 16-byte phase): the staged tile route (bitmap + block copies,
+    two-phase boundary words) == the byte-wise route == the definition, and no byte outside a domain's slot range is
+    written (the slot layout's padding stays zero)."""
+    rng = np.random.default_rng(11 + host_nodes)
+    paths = []
+    for i in range(700):
+        kind = i % 7
+        ln = int(rng.integers(0, 6)) if kind == 0 else int(rng.integers(0, 40)) if kind < 5 else int(rng.integers(60, 300))
+        alphabet = [b"/ab", b"/abcdefgh\x80\xff.", b"//a", b"abcdefghijklmnopqrstuvwxyz0123456789-/"][int(rng.integers(0, 4))]
+        body = bytes(alphabet[int(x)] for x in rng.integers(0, len(alphabet), ln))
+        paths.append((b"/" if rng.random() < 0.9 else b"") + body)
+    got = {}
+    for bytewise in (False, True):
+        rec, dom, _, po, _ = run(emul, None, paths, host_nodes=host_nodes, bytewise=bytewise)
+        for i, p in enumerate(paths):
+            ok, want, hp, hl = path_expect(p, host_nodes)
+            assert bool(rec["flags"][i] & DEC_PATH_OK) == ok, (p, bytewise)
+            a = int(po[i])
+            if ok:
+                assert int(rec["dom_len"][i]) == len(want) and bytes(dom[a:a + len(want)]) == want, (p, bytewise)
+                if host_nodes:
+                    assert (int(rec["host_pos"][i]), int(rec["host_len"][i])) == (hp, hl)
+            used = len(want) if ok else 0
+            assert not dom[a + used:int(po[i + 1])].any(), (p, bytewise, "padding written")
+        got[bytewise] = (rec.copy(), dom.copy())
+    assert np.array_equal(got[False][0], got[True][0]) and np.array_equal(got[False][1], got[True][1])
