@@ -2056,7 +2056,7 @@ int regk_parent_dirs(regk_ctx *ctx, uint32_t flags, regk_parents *out)
     const size_t totals_bytes = ((ntiles * 4 + 15) & ~(size_t)15) + (ntiles / SUPER + 1) * 8 + 16;
     int rc;
     if ((rc = ensure_dev(ctx, ctx->par_len, n * 4)) || (rc = ensure_dev(ctx, ctx->par_slot, n * 4)) ||
-        (rc = ensure_dev(ctx, ctx->par_table, slots * 8)) || (rc = ensure_dev(ctx, ctx->par_totals, totals_bytes)) ||
+        (rc = ensure_dev(ctx, ctx->par_table, slots * 4)) || (rc = ensure_dev(ctx, ctx->par_totals, totals_bytes)) ||
         (rc = ensure_dev(ctx, ctx->par_unique, n * 8 + 8)) || (rc = ensure_host(ctx, ctx->h_par_count, 8)))
         return rc;
     ParentParams p{};
@@ -2066,7 +2066,6 @@ int regk_parent_dirs(regk_ctx *ctx, uint32_t flags, regk_parents *out)
     p.parent_len = (uint32_t *)ctx->par_len.p;
     p.slot_of = (uint32_t *)ctx->par_slot.p;
     p.owner = (uint32_t *)ctx->par_table.p;
-    p.first = p.owner + slots;
     p.mask = (uint32_t)(slots - 1);
     p.tile_total = (uint32_t *)ctx->par_totals.p;
     p.super_total = (unsigned long long *)((uint8_t *)ctx->par_totals.p + ((ntiles * 4 + 15) & ~(size_t)15));
@@ -2081,7 +2080,6 @@ int regk_parent_dirs(regk_ctx *ctx, uint32_t flags, regk_parents *out)
     }
     cudaEvent_t e0 = ctx->par_ev[0], e1 = ctx->par_ev[1];
     CK(cudaMemsetAsync(p.owner, 0, slots * 4, s));
-    CK(cudaMemsetAsync(p.first, 0xFF, slots * 4, s));
     CK(cudaMemsetAsync(ctx->par_totals.p, 0, totals_bytes, s));
     CK(cudaEventRecord(e0, s));
     regk_parent_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p);

@@ -12,12 +12,16 @@
  *
  * Kernels: (1) regk_parent_kernel - one thread per record: the directory length (host nodes: the path minus
  * its hostname and separator, no scan; alias nodes: backward scan), a word-wise 32-bit hash of the prefix
- * (composers in regk_core.cuh, emulated on the CPU by tests/emul), insert into an open-addressing table whose slots hold "owner record + 1" (claimed by
- * one atomicCAS, so the owner is stable the moment it is visible); a record that meets a claimed slot
- * compares its prefix with the owner's bytes - equal: same directory (atomicMin of the first index),
- * different: next slot.  (2) regk_parent_mark_kernel - a record is a first occurrence iff the table says
- * so; per-tile counts go into two-level totals.  (3) regk_parent_compact_kernel - each tile derives its base
- * from the totals and writes its first-occurrence indices in order.
+ * (composers in regk_core.cuh, emulated on the CPU by tests/emul), insert into an open-addressing table whose slots
+ * hold "record + 1" of SOME record with the slot's directory: an empty slot is claimed by one atomicCAS; a record that
+ * meets a claimed slot compares its prefix with that record's bytes - equal: same directory, and the slot keeps the
+ * smaller index (atomicMin - the directory a slot stands for never changes, only its representative); different: next
+ * slot.  So when the kernel is done a slot holds the FIRST occurrence of its directory - one table, one random access
+ * per record (the first version kept owner and first index in two tables and paid two).  (2) regk_parent_mark_kernel -
+ * a record is a first occurrence iff its slot names it; the flag replaces slot_of[i] (so the third kernel reads it
+ * coalesced instead of going through the table again), per-tile counts go into two-level totals.
+ * (3) regk_parent_compact_kernel - each tile derives its base from the totals and writes its first-occurrence
+ * indices in order.
  */
 #pragma once
 
@@ -31,9 +35,10 @@ struct ParentParams {
     const uint8_t *path_bytes;
     const unsigned long long *path_off;         /* [n + 1] */
     uint32_t *parent_len;                       /* [n] */
-    uint32_t *slot_of;                          /* [n] the table slot of record i's directory */
-    uint32_t *owner;                            /* [slots] record + 1, 0 = empty (zeroed by the host) */
-    uint32_t *first;                            /* [slots] smallest record index with this directory (0xFFFFFFFF-filled) */
+    uint32_t *slot_of;                          /* [n] the table slot of record i's directory; after the mark kernel: 1 iff
+                                                   record i is the first occurrence of its directory */
+    uint32_t *owner;                            /* [slots] record + 1 of the smallest record seen with this directory,
+                                                   0 = empty (zeroed by the host) */
     uint32_t mask;                              /* slots - 1 (power of two) */
     uint32_t *tile_total;                       /* [ntiles] first occurrences per tile */
     unsigned long long *super_total;            /* [ntiles / SUPER + 1] */
@@ -74,19 +79,20 @@ __global__ void __launch_bounds__(256) regk_parent_kernel(const ParentParams p)
             if (cur == 0u)
                 break;                                      /* claimed: this record owns the slot */
         }
-        const uint64_t j = cur - 1u;                        /* the owner is final once visible */
+        const uint64_t j = cur - 1u;                        /* whoever it is, it has the slot's directory */
         if (j == i)
             break;
-        /* compare with the owner's directory, derived from its own path (its parent_len may not be stored yet) */
+        /* compare with that record's directory, derived from its own path (its parent_len may not be stored yet) */
         const unsigned long long q0 = p.path_off[j], q1 = p.path_off[j + 1];
         const uint32_t tpl = parent_length(p, j, p.path_bytes + q0, (uint32_t)(q1 - q0));
-        if (tpl == plen && string_equal(W, o0, q0, plen))
+        if (tpl == plen && string_equal(W, o0, q0, plen)) {
+            if (cur > (uint32_t)i + 1u)                     /* values only fall: a smaller one needs no update */
+                atomicMin(p.owner + slot, (uint32_t)i + 1u);
             break;                                          /* same directory */
+        }
         slot = (slot + 1u) & p.mask;
     }
     p.slot_of[i] = slot;
-    if (p.first[slot] > (uint32_t)i)
-        atomicMin(p.first + slot, (uint32_t)i);
 }
 
 constexpr uint32_t PARENT_TILE = 256;
@@ -95,8 +101,10 @@ __global__ void __launch_bounds__(PARENT_TILE) regk_parent_mark_kernel(const Par
 {
     const uint64_t i = (uint64_t)blockIdx.x * PARENT_TILE + threadIdx.x;
     uint32_t is_first = 0;
-    if (i < p.n)
-        is_first = p.first[p.slot_of[i]] == (uint32_t)i ? 1u : 0u;
+    if (i < p.n) {
+        is_first = p.owner[p.slot_of[i]] == (uint32_t)i + 1u ? 1u : 0u;
+        p.slot_of[i] = is_first;
+    }
     uint32_t cnt = __popc(__ballot_sync(0xFFFFFFFFu, is_first));
     if ((threadIdx.x & 31u) == 0)
         add_tile_total(p.tile_total, p.super_total, blockIdx.x, cnt);
@@ -115,7 +123,7 @@ __global__ void __launch_bounds__(PARENT_TILE) regk_parent_compact_kernel(const 
     const uint64_t i = (uint64_t)tile * PARENT_TILE + threadIdx.x;
     uint32_t is_first = 0;
     if (i < p.n)
-        is_first = p.first[p.slot_of[i]] == (uint32_t)i ? 1u : 0u;
+        is_first = p.slot_of[i];
     __syncthreads();
     /* block-wide exclusive scan of the flags (same shape as block_scan in regk_kernels.cuh, 8 warps) */
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
