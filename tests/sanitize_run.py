@@ -49,6 +49,15 @@ b = synth.generate("config5", n=2100, start=11)
 res = ctx.register_batch(b)
 fb, fo, _ = ctx.jute_frames(xid_base=9, zk_flags=1)
 assert bytes(fb) == b"".join(pyoracle.jute_create_request(res.path(i), res.json(i), 9 + i, 1) for i in range(b.n))
+for op, group in ((2, 0), (5, 0), (1, 7), (2, 100)):             # delete / setData requests, multi transactions
+    fb, fo, _ = ctx.jute_requests(op=op, xid_base=3, group=group)
+    data = (lambda i: res.json(i)) if op != 2 else (lambda i: b"")
+    if group == 0:
+        want = b"".join(pyoracle.jute_request(op, res.path(i), data(i), 3 + i) for i in range(b.n))
+    else:
+        want = b"".join(pyoracle.jute_multi(op, [(res.path(i), data(i)) for i in range(a, min(a + group, b.n))], 3 + k)
+                        for k, a in enumerate(range(0, b.n, group)))
+    assert bytes(fb) == want
 rec, dom, ports, _ = ctx.decode(last=True, host_nodes=True)
 assert np.all(rec["flags"] == 3) and np.array_equal(rec["dom_len"], np.diff(b.domain_off.astype(np.int64)))
 rec2, _, _, _ = ctx.decode(res.path_bytes, res.path_off, res.json_bytes, res.json_off, host_nodes=True)
