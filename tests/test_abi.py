@@ -53,6 +53,7 @@ def test_struct_layouts_match_header(built):
                sizeof(regk_frames), offsetof(regk_frames, kernel_ms), sizeof(regk_decoded), sizeof(regk_decode_in),
                offsetof(regk_decode_in, json_off), sizeof(regk_decode_out), offsetof(regk_decode_out, ports),
                offsetof(regk_decode_out, kernel_ms));
+        printf("%zu %zu %zu ", sizeof(regk_jute_opts), offsetof(regk_jute_opts, version), offsetof(regk_jute_opts, group));
         printf("%zu %zu %zu %zu %zu ", sizeof(regk_job), offsetof(regk_job, mailbox), offsetof(regk_job, timeout_ms),
                offsetof(regk_result, job_path_base), offsetof(regk_result, json_off32));
         printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(regk_batch), offsetof(regk_batch, domain_bytes),
@@ -70,6 +71,7 @@ def test_struct_layouts_match_header(built):
            _native.CFrames.kernel_ms.offset, _native.DECODED_DTYPE.itemsize, C.sizeof(_native.CDecodeIn),
            _native.CDecodeIn.json_off.offset, C.sizeof(_native.CDecodeOut), _native.CDecodeOut.ports.offset,
            _native.CDecodeOut.kernel_ms.offset,
+           C.sizeof(_native.CJuteOpts), _native.CJuteOpts.version.offset, _native.CJuteOpts.group.offset,
            C.sizeof(_native.CJob), _native.CJob.mailbox.offset, _native.CJob.timeout_ms.offset,
            _native.CResult.job_path_base.offset, _native.CResult.json_off32.offset,
            C.sizeof(_native.CBatch), _native.CBatch.domain_bytes.offset, _native.CBatch.ports_present.offset,
