@@ -126,6 +126,23 @@ def test_gpu_jute_requests_and_transactions(ctx, op, group):
 
 
 @pytest.mark.gpu
+def test_gpu_jute_requests_random_shapes(ctx):
+    """40 random (configuration, batch size, operation, group size, xid base) combinations against the restatement."""
+    rng = np.random.default_rng(2024)
+    for _ in range(40):
+        cfg = ["config1", "config3", "config5"][int(rng.integers(0, 3))]
+        n = int(rng.integers(1, 900))
+        op = [1, 2, 5][int(rng.integers(0, 3))]
+        group = [0, 1, 2, 3, 5, 31, 63, 64, 65, 127, 128, 129, 300, 1000][int(rng.integers(0, 14))]
+        xid = int(rng.integers(-2 ** 31, 2 ** 31 - 70000))
+        flags, version = int(rng.integers(0, 4)), int(rng.integers(-1, 50))
+        res = ctx.register_batch(synth.generate(cfg, n=n, start=int(rng.integers(0, 10 ** 6))))
+        fb, fo, _ = ctx.jute_requests(op=op, xid_base=xid, zk_flags=flags, version=version, group=group)
+        want, woff = requests_of(res, op, xid, group, flags, version)
+        assert np.array_equal(fo, woff) and bytes(fb) == want, (cfg, n, op, group, xid, flags, version)
+
+
+@pytest.mark.gpu
 def test_gpu_jute_requests_edges(ctx):
     from registrar_b200._native import RegkError
     recs = [{"domain": "a.b", "hostname": "h", "type": "host", "address": "1.2.3.4"}]
@@ -263,3 +280,67 @@ def test_gpu_service_records_decode_back(ctx):
     assert np.array_equal(ports[(res.json_off[:-1] >> np.uint64(1)).astype(np.int64)], sb.port)
     assert np.array_equal(rec["type_len"], np.diff(sb.srvce_off.astype(np.int64)))
     assert np.array_equal(rec["addr_len"], np.diff(sb.proto_off.astype(np.int64)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host_nodes", [True, False])
+def test_gpu_reader_equals_its_host_build_on_arbitrary_streams(ctx, emul, host_nodes):
+    """The kernel (staged tiles, shared-memory regions used twice, two-phase boundary words) against the SAME per-record
+    code compiled for the host (tests/emul, itself fuzzed against independent definitions in tests/test_decode_emul.py):
+    random byte strings as paths and single-byte mutations of real payloads - every field of every result record, every
+    domain byte and every port must agree, for valid and invalid records alike."""
+    import ctypes as C
+    from registrar_b200._native import DECODED_DTYPE, DEC_HOST_RECORD, DEC_SERVICE_RECORD, DEC_PATH_OK
+    rng = np.random.default_rng(77 + host_nodes)
+    res = oracle.register_batch(synth.generate("config5", n=1500, start=3))
+    payloads, paths = [], []
+    alphabet = b'{}[]",:\\0123456789-.eE tarsxyz'
+    for i in range(res.n):
+        q = bytearray(res.json(i))
+        if i % 3:
+            pos, kind = int(rng.integers(0, len(q))), int(rng.integers(0, 4))
+            c = alphabet[int(rng.integers(0, len(alphabet)))]
+            if kind == 0:
+                q[pos] = c
+            elif kind == 1:
+                del q[pos]
+            elif kind == 2:
+                q.insert(pos, c)
+            else:
+                q = q[:pos]
+        payloads.append(bytes(q))
+        if i % 4 == 0:
+            paths.append(res.path(i))
+        else:
+            ln = int(rng.integers(0, 30)) if i % 4 < 3 else int(rng.integers(60, 260))
+            ab = [b"/ab", b"/abcdefgh\x80\xff.", b"//a", b"abcdefghijklmnopqrstuvwxyz0123456789-/"][int(rng.integers(0, 4))]
+            paths.append((b"/" if rng.random() < 0.9 else b"") + bytes(ab[int(x)] for x in rng.integers(0, len(ab), ln)))
+
+    def streams(items):
+        off = np.zeros(len(items) + 1, np.uint64)
+        off[1:] = np.cumsum([len(x) for x in items])
+        return np.frombuffer(b"".join(items) + b"\0" * 8, np.uint8).copy(), off
+    pb, po = streams(paths)
+    jb, jo = streams(payloads)
+    n = len(paths)
+    want = np.zeros(n * 10, np.uint32)
+    wdom = np.zeros(int(po[-1]) + 16, np.uint8)
+    wports = np.zeros(int(jo[-1]) // 2 + 16, np.uint32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    emul.emul_decode(C.c_uint64(n), vp(pb), vp(po), vp(jb), vp(jo), C.c_int(1 if host_nodes else 0), vp(want), vp(wdom), vp(wports))
+    want = want.view(DECODED_DTYPE)
+    rec, dom, ports, _ = ctx.decode(pb[:int(po[-1])], po, jb[:int(jo[-1])], jo, host_nodes=host_nodes)
+    assert np.array_equal(rec["flags"], want["flags"])
+    assert (rec["flags"] & DEC_PATH_OK).any() and not (rec["flags"] & DEC_PATH_OK).all()
+    for i in range(n):
+        f = int(rec["flags"][i])
+        if f & DEC_PATH_OK:
+            assert (rec["dom_len"][i], rec["host_pos"][i], rec["host_len"][i]) == (want["dom_len"][i], want["host_pos"][i], want["host_len"][i])
+            a, ln = int(po[i]), int(rec["dom_len"][i])
+            assert np.array_equal(dom[a:a + ln], wdom[a:a + ln]), paths[i]
+        if f & (DEC_HOST_RECORD | DEC_SERVICE_RECORD):
+            for k in ("type_pos", "type_len", "addr_pos", "addr_len", "ttl", "nports"):
+                assert rec[k][i] == want[k][i], (k, payloads[i])
+            if rec["nports"][i] != 0xFFFFFFFF:
+                a = int(jo[i]) >> 1
+                assert np.array_equal(ports[a:a + int(rec["nports"][i])], wports[a:a + int(rec["nports"][i])])
