@@ -344,3 +344,30 @@ def test_gpu_reader_equals_its_host_build_on_arbitrary_streams(ctx, emul, host_n
             if rec["nports"][i] != 0xFFFFFFFF:
                 a = int(jo[i]) >> 1
                 assert np.array_equal(ports[a:a + int(rec["nports"][i])], wports[a:a + int(rec["nports"][i])])
+
+
+@pytest.mark.gpu
+def test_gpu_reader_on_the_callers_own_device_streams(ctx):
+    """REGK_IN_DEVICE: streams in device buffers that end exactly where the data ends (no slack behind the last byte) -
+    the tiles at the end of the streams must take the guarded byte-wise route and still agree with the staged one."""
+    import ctypes as C
+    import torch
+    from registrar_b200 import _native as nv
+    res = ctx.register_batch(synth.generate("config3", n=5000, start=9))
+    want, wdom, wports, _ = ctx.decode(res.path_bytes, res.path_off, res.json_bytes, res.json_off, host_nodes=True)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in
+           (res.path_bytes[:res.path_total], res.path_off.astype(np.uint64).view(np.int64),
+            res.json_bytes[:res.json_total], res.json_off.astype(np.uint64).view(np.int64))]
+    torch.cuda.synchronize()
+    cin = nv.CDecodeIn(n=res.n, flags=nv.FLAG_IN_DEVICE, host_nodes=1, path_total=res.path_total, json_total=res.json_total,
+                       path_bytes=dev[0].data_ptr(), path_off=dev[1].data_ptr(), json_bytes=dev[2].data_ptr(),
+                       json_off=dev[3].data_ptr())
+    out = nv.CDecodeOut()
+    ctx._check(ctx._lib.regk_decode(ctx._h, C.byref(cin), C.byref(out)))
+    n = int(out.n)
+    rec = np.frombuffer((C.c_uint8 * (n * nv.DECODED_DTYPE.itemsize)).from_address(out.rec), dtype=nv.DECODED_DTYPE, count=n)
+    assert np.array_equal(rec, want)
+    dom = nv._as_np(out.dom_bytes, int(out.dom_bytes_len), np.uint8)
+    for i in (0, 1, n // 2, n - 2, n - 1):
+        a = int(res.path_off[i])
+        assert np.array_equal(dom[a:a + int(rec["dom_len"][i])], wdom[a:a + int(rec["dom_len"][i])])
