@@ -135,6 +135,15 @@ def test_encoder_output_is_recognised_and_mutations_are_not(emul):
              b'{"type":"host","address":"1","host":{"address":"1","ports":[-1]}}',
              b'{"type":"service","service":{"type":"service","service":{"srvce":"a","srvce":"b","proto":"c","port":1}}}',
              b'{"type":"service","service":{"type":"service","service":{"srvce":"a","proto":"c","port":1,}}}']
+    # integers of every length on both sides of the 8-byte window of the digit parser, and of the ranges
+    for v in [0, 7, 42, 999, 1000, 65535, 99999, 100000, 1234567, 9999999, 10000000, 12345678, 99999999, 100000000,
+              123456789, 2147483647, 2147483648, 4294967295, 4294967296, 99999999999, 100000000000, 123456789012]:
+        extra.append(b'{"type":"host","address":"1","host":{"address":"1","ports":[%d]}}' % v)
+        extra.append(b'{"type":"host","address":"1","host":{"address":"1","ports":[5,%d,6]}}' % v)
+        extra.append(b'{"type":"host","address":"1","ttl":%d,"host":{"address":"1"}}' % v)
+        extra.append(b'{"type":"host","address":"1","ttl":-%d,"host":{"address":"1"}}' % v)
+        extra.append(b'{"type":"host","address":"1","ttl":0%d,"host":{"address":"1"}}' % v)
+        extra.append(b'{"type":"host","address":"1","ttl":%d.5,"host":{"address":"1"}}' % v)
     items = base + mutated + extra
     for bytewise in (False, True):                                  # the staged route's cursor and the guarded one
         rec, _, ports, _, jo = run(emul, items, bytewise=bytewise)
